@@ -1,0 +1,158 @@
+// api.cu -- the C ABI (include/b200sort.h): argument checks, key-type -> bit-transform mapping, dispatch to the
+// per-(key width, value width) instantiations, and the host-pointer convenience wrappers.
+#include <cuda_runtime.h>
+#include <mutex>
+#include "../../include/b200sort.h"
+#include "common.cuh"
+#include "sort_api.h"
+
+using namespace b200;
+
+namespace {
+
+bool make_twiddle(int key_type, int descending, Twiddle* tw, int* key_bytes) {
+  Twiddle t{0, 0, 0};
+  switch (key_type) {
+    case B200_KEY_U32: *key_bytes = 4; break;
+    case B200_KEY_U64: *key_bytes = 8; break;
+    case B200_KEY_I32: *key_bytes = 4; t.sign_mask = 0x80000000ull; break;
+    case B200_KEY_I64: *key_bytes = 8; t.sign_mask = 0x8000000000000000ull; break;
+    case B200_KEY_F32: *key_bytes = 4; t.sign_mask = 0x80000000ull; t.float_mask = 0xFFFFFFFFull; break;
+    case B200_KEY_F64: *key_bytes = 8; t.sign_mask = 0x8000000000000000ull; t.float_mask = ~0ull; break;
+    default: return false;
+  }
+  if (descending) t.flip_mask = (*key_bytes == 4) ? 0xFFFFFFFFull : ~0ull;
+  *tw = t;
+  return true;
+}
+
+#define DISPATCH_KV(KB, VB, CALL)                                    \
+  do {                                                               \
+    if ((KB) == 4 && (VB) == 0) { using K = uint32_t; constexpr int V = 0; return (int)(CALL); } \
+    if ((KB) == 4 && (VB) == 4) { using K = uint32_t; constexpr int V = 4; return (int)(CALL); } \
+    if ((KB) == 4 && (VB) == 8) { using K = uint32_t; constexpr int V = 8; return (int)(CALL); } \
+    if ((KB) == 8 && (VB) == 0) { using K = uint64_t; constexpr int V = 0; return (int)(CALL); } \
+    if ((KB) == 8 && (VB) == 4) { using K = uint64_t; constexpr int V = 4; return (int)(CALL); } \
+    if ((KB) == 8 && (VB) == 8) { using K = uint64_t; constexpr int V = 8; return (int)(CALL); } \
+    return (int)cudaErrorInvalidValue;                               \
+  } while (0)
+
+// grow-only device scratch for the host-pointer wrappers (one set per process; serialised by a mutex)
+struct HostPathCache {
+  std::mutex mu;
+  void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[5] = {0, 0, 0, 0, 0};
+  cudaStream_t stream = nullptr;
+  cudaError_t need(int i, size_t bytes) {
+    if (bytes <= cap[i]) return cudaSuccess;
+    if (buf[i]) cudaFree(buf[i]);
+    buf[i] = nullptr; cap[i] = 0;
+    cudaError_t e = cudaMalloc(&buf[i], bytes);
+    if (e == cudaSuccess) cap[i] = bytes;
+    return e;
+  }
+};
+HostPathCache g_cache;
+
+int sort_host(bool msb, const void* hk, const void* hv, uint64_t n, void* hko, void* hvo, int key_type, int value_bytes, int descending) {
+  Twiddle tw; int kb;
+  if (!make_twiddle(key_type, descending, &tw, &kb)) return (int)cudaErrorInvalidValue;
+  if (value_bytes != 0 && value_bytes != 4 && value_bytes != 8) return (int)cudaErrorInvalidValue;
+  if ((value_bytes != 0) != (hv != nullptr)) return (int)cudaErrorInvalidValue;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lock(g_cache.mu);
+  cudaError_t e;
+  if (!g_cache.stream && (e = cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+  cudaStream_t s = g_cache.stream;
+  size_t ws = 0;
+  if (msb) e = (cudaError_t)b200_msb_sort(nullptr, nullptr, n, nullptr, nullptr, key_type, value_bytes, nullptr, &ws, s, nullptr, nullptr);
+  else e = (cudaError_t)b200_lsb_sort(nullptr, &ws, nullptr, nullptr, nullptr, nullptr, nullptr, n, key_type, value_bytes, 0, kb * 8, descending, 1, s);
+  if (e != cudaSuccess) return (int)e;
+  if ((e = g_cache.need(0, n * kb)) != cudaSuccess) return (int)e;
+  if ((e = g_cache.need(1, n * kb)) != cudaSuccess) return (int)e;
+  if (value_bytes) {
+    if ((e = g_cache.need(2, n * value_bytes)) != cudaSuccess) return (int)e;
+    if ((e = g_cache.need(3, n * value_bytes)) != cudaSuccess) return (int)e;
+  }
+  if ((e = g_cache.need(4, ws)) != cudaSuccess) return (int)e;
+  void *k0 = g_cache.buf[0], *k1 = g_cache.buf[1], *v0 = value_bytes ? g_cache.buf[2] : nullptr, *v1 = value_bytes ? g_cache.buf[3] : nullptr;
+  if ((e = cudaMemcpyAsync(k0, hk, n * kb, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+  if (value_bytes && (e = cudaMemcpyAsync(v0, hv, n * value_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+  void *rk = k0, *rv = v0;
+  if (msb) {
+    e = (cudaError_t)b200_msb_sort(k0, v0, n, k1, v1, key_type, value_bytes, g_cache.buf[4], &ws, s, &rk, &rv);
+  } else {
+    int sel = 0;
+    e = (cudaError_t)b200_lsb_sort(g_cache.buf[4], &ws, k0, k1, v0, v1, &sel, n, key_type, value_bytes, 0, kb * 8, descending, 1, s);
+    if (sel) { rk = k1; rv = v1; }
+  }
+  if (e != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpyAsync(hko, rk, n * kb, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
+  if (value_bytes && (e = cudaMemcpyAsync(hvo, rv, n * value_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
+  return (int)cudaStreamSynchronize(s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_version(void) { return 100; }
+
+const char* b200_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
+
+int b200_lsb_sort(void* d_temp, size_t* temp_bytes, void* d_keys_current, void* d_keys_alternate, void* d_values_current,
+                  void* d_values_alternate, int* selector_out, uint64_t num_items, int key_type, int value_bytes,
+                  int begin_bit, int end_bit, int descending, int allow_overwrite, b200_stream_t stream) {
+  Twiddle tw; int kb;
+  if (!make_twiddle(key_type, descending, &tw, &kb) || temp_bytes == nullptr) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_KV(kb, value_bytes, (lsb_sort_impl<K, V>(d_temp, temp_bytes, d_keys_current, d_keys_alternate, d_values_current,
+                                                    d_values_alternate, selector_out, num_items, tw, begin_bit, end_bit,
+                                                    allow_overwrite, s)));
+}
+
+int b200_msb_sort(void* d_keys, void* d_values, uint64_t num_items, void* d_keys_alt, void* d_values_alt, int key_type,
+                  int value_bytes, void* d_workspace, size_t* workspace_bytes, b200_stream_t stream, void** out_keys,
+                  void** out_values) {
+  Twiddle tw; int kb;
+  if (!make_twiddle(key_type, 0, &tw, &kb)) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d_workspace == nullptr && workspace_bytes == nullptr) {
+    // reference default: temporary memory lives and dies inside the call (stream-ordered here, no host sync)
+    size_t ws = 0;
+    int e = b200_msb_sort(nullptr, nullptr, num_items, nullptr, nullptr, key_type, value_bytes, nullptr, &ws, stream, nullptr, nullptr);
+    if (e) return e;
+    void* w = nullptr;
+    cudaError_t ce = cudaMallocAsync(&w, ws, s);
+    if (ce != cudaSuccess) return (int)ce;
+    e = b200_msb_sort(d_keys, d_values, num_items, d_keys_alt, d_values_alt, key_type, value_bytes, w, &ws, stream, out_keys, out_values);
+    ce = cudaFreeAsync(w, s);
+    return e ? e : (int)ce;
+  }
+  if (workspace_bytes == nullptr) return (int)cudaErrorInvalidValue;
+  DISPATCH_KV(kb, value_bytes, (msb_sort_impl<K, V>(d_keys, d_values, num_items, d_keys_alt, d_values_alt, tw, d_workspace,
+                                                    workspace_bytes, s, out_keys, out_values)));
+}
+
+int b200_msb_sort_host(const void* h_keys, const void* h_values, uint64_t num_items, void* h_sorted_keys, void* h_sorted_values,
+                       int key_type, int value_bytes) {
+  return sort_host(true, h_keys, h_values, num_items, h_sorted_keys, h_sorted_values, key_type, value_bytes, 0);
+}
+int b200_lsb_sort_host(const void* h_keys, const void* h_values, uint64_t num_items, void* h_sorted_keys, void* h_sorted_values,
+                       int key_type, int value_bytes, int descending) {
+  return sort_host(false, h_keys, h_values, num_items, h_sorted_keys, h_sorted_values, key_type, value_bytes, descending);
+}
+
+int b200_range_partition(void* d_temp, size_t* temp_bytes, const void* d_keys_in, const void* d_values_in, void* d_keys_out,
+                         void* d_values_out, uint64_t num_items, int key_type, int value_bytes, int bits,
+                         const uint32_t* d_splitters, int num_parts, const uint64_t* d_local_counts, uint64_t* d_part_offsets,
+                         b200_stream_t stream) {
+  Twiddle tw; int kb;
+  if (!make_twiddle(key_type, 0, &tw, &kb) || temp_bytes == nullptr) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_KV(kb, value_bytes, (range_partition_impl<K, V>(d_temp, temp_bytes, d_keys_in, d_values_in, d_keys_out, d_values_out,
+                                                           num_items, tw, bits, d_splitters, num_parts, d_local_counts,
+                                                           d_part_offsets, s)));
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+// msb_sched.cuh -- device-side scheduling of the MSB hybrid sort.  Replaces, without any host round trip,
+//   do_fast_merged_compute_subbin_offsets_and_segmented_next_pass_assignments
+//       (msb/src/sort/cuda_radix_sort.h:982-1271: prefix sums + classify/merge sub-buckets + emit work lists) and
+//   generate_next_pass_block_assignments (HOST code in the reference, msb/src/sort/gpu_radix_sort.cu:29-104).
+// Per level: classify_kernel turns every segment's histogram into digit starts, emits the next level's segments
+// (sub-buckets larger than the on-chip capacity) and the local-sort work items (everything else; runs of tiny
+// neighbours are merged into one item, reference threshold RDXSRT_CFG_MERGE_LOCREC_THRESH,
+// cuda_radix_sort_config.h:4); scan_tiles_kernel + fill_descs_kernel cut the next level's segments into tiles.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum { ERR_SEG_OVERFLOW = 1, ERR_LOCAL_OVERFLOW = 2, ERR_TILE_OVERFLOW = 4 };
+
+struct MsbCounters {            // one small zero-initialised block in the workspace
+  uint32_t num_segs[10];        // per level
+  uint32_t num_tiles[10];
+  uint32_t part_ticket[10];
+  uint32_t num_locals;
+  uint32_t local_ticket;
+  uint32_t error;
+  uint32_t pad;
+};
+
+static __global__ void msb_init_kernel(Seg* segs, MsbCounters* c, uint64_t n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    segs[0].off = 0; segs[0].cnt = n;
+    c->num_segs[0] = 1;
+  }
+}
+
+struct ClassifyArgs {
+  const Seg* segs; const uint32_t* num_segs_ptr;
+  const uint32_t* seg_hist;     // [segment][256]
+  uint64_t* bins;               // [segment][256] out: absolute start of every sub-bucket
+  Seg* next_segs; uint32_t* num_next_ptr; uint32_t max_segs;
+  LocalItem* locals; uint32_t* num_locals_ptr; uint32_t max_locals;
+  uint32_t* error;
+  int shift;                    // bit position of this level's digit; `shift` low bits remain below it
+  uint32_t local_cap, merge_cap;
+  uint32_t out_buf;             // ping-pong buffer the level scatters into
+};
+
+constexpr int CLS_WARPS = 4;
+
+static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const __grid_constant__ ClassifyArgs a) {
+  __shared__ uint32_t s_cnt[CLS_WARPS][RADIX];
+  __shared__ uint64_t s_off[CLS_WARPS][RADIX];
+  __shared__ LocalItem s_loc[CLS_WARPS][RADIX];
+  __shared__ Seg s_seg[CLS_WARPS][RADIX];
+  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const uint32_t num_segs = *a.num_segs_ptr;
+  for (uint32_t s = blockIdx.x * CLS_WARPS + w; s < num_segs; s += gridDim.x * CLS_WARPS) {
+    const Seg sg = a.segs[s];
+    // exclusive scan of the 256 counts: lane owns digits 8*lane .. 8*lane+7
+    uint32_t c[8]; uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] = a.seg_hist[(uint64_t)s * RADIX + lane * 8 + i]; sum += c[i]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (unsigned)o) inc += t;
+    }
+    uint64_t run = sg.off + (inc - sum);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a.bins[(uint64_t)s * RADIX + lane * 8 + i] = run;
+      s_cnt[w][lane * 8 + i] = c[i];
+      s_off[w][lane * 8 + i] = run;
+      run += c[i];
+    }
+    __syncwarp();
+    if (a.shift == 0) continue;       // last digit: every sub-bucket is final after the scatter
+    // classify + merge, serial over the 256 digits (lane 0), staged in shared memory
+    uint32_t nloc = 0, nseg = 0;
+    if (lane == 0) {
+      uint64_t pend_off = 0; uint32_t pend_sum = 0, pend_n = 0;
+      auto flush = [&]() {
+        if (pend_n) {
+          LocalItem it; it.off = pend_off; it.cnt = pend_sum;
+          it.nbits = (uint16_t)(pend_n > 1 ? a.shift + 8 : a.shift); it.src = (uint16_t)a.out_buf;
+          s_loc[w][nloc++] = it;
+          pend_n = 0; pend_sum = 0;
+        }
+      };
+      for (int d = 0; d < RADIX; ++d) {
+        const uint32_t cd = s_cnt[w][d];
+        if (cd == 0) continue;
+        if (cd > a.local_cap) {
+          flush();
+          Seg ns; ns.off = s_off[w][d]; ns.cnt = cd;
+          s_seg[w][nseg++] = ns;
+        } else if (cd > a.merge_cap) {
+          flush();
+          LocalItem it; it.off = s_off[w][d]; it.cnt = cd; it.nbits = (uint16_t)a.shift; it.src = (uint16_t)a.out_buf;
+          s_loc[w][nloc++] = it;
+        } else {
+          if (pend_n && pend_sum + cd > a.merge_cap) flush();
+          if (pend_n == 0) pend_off = s_off[w][d];
+          pend_sum += cd; ++pend_n;
+        }
+      }
+      flush();
+    }
+    nloc = __shfl_sync(0xffffffffu, nloc, 0);
+    nseg = __shfl_sync(0xffffffffu, nseg, 0);
+    __syncwarp();
+    uint32_t lbase = 0, sbase = 0;
+    if (lane == 0) {
+      if (nloc) lbase = atomicAdd(a.num_locals_ptr, nloc);
+      if (nseg) sbase = atomicAdd(a.num_next_ptr, nseg);
+    }
+    lbase = __shfl_sync(0xffffffffu, lbase, 0);
+    sbase = __shfl_sync(0xffffffffu, sbase, 0);
+    if (lbase + nloc > a.max_locals) { if (lane == 0) atomicOr(a.error, (uint32_t)ERR_LOCAL_OVERFLOW); nloc = 0; }
+    if (sbase + nseg > a.max_segs) { if (lane == 0) atomicOr(a.error, (uint32_t)ERR_SEG_OVERFLOW); nseg = 0; }
+    for (uint32_t i = lane; i < nloc; i += 32) a.locals[lbase + i] = s_loc[w][i];
+    for (uint32_t i = lane; i < nseg; i += 32) a.next_segs[sbase + i] = s_seg[w][i];
+    __syncwarp();
+  }
+}
+
+// Exclusive scan of tiles-per-segment -> tile_base[0..num_segs], total -> *num_tiles_ptr.  ONE CTA.
+constexpr int SCAN_THREADS = 1024;
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const Seg* segs, const uint32_t* num_segs_ptr, uint32_t* tile_base,
+                                                                   uint32_t* num_tiles_ptr, uint32_t max_tiles, uint32_t* error, int tile) {
+  __shared__ uint32_t s_w[32];
+  const uint32_t ns = min(*num_segs_ptr, 0x7fffffffu);
+  const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const uint32_t per = (ns + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t s0 = min(per * tid, ns), s1 = min(s0 + per, ns);
+  uint32_t sum = 0;
+  for (uint32_t s = s0; s < s1; ++s) sum += (uint32_t)((segs[s].cnt + tile - 1) / tile);
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (unsigned)o) inc += t;
+  }
+  if (lane == 31) s_w[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t v = s_w[lane], vi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+      if (lane >= (unsigned)o) vi += t;
+    }
+    s_w[lane] = vi - v;
+    if (lane == 31) {
+      uint32_t total = vi;
+      if (total > max_tiles) { atomicOr(error, (uint32_t)ERR_TILE_OVERFLOW); total = 0; }
+      *num_tiles_ptr = total;
+      tile_base[ns] = total;
+    }
+  }
+  __syncthreads();
+  uint32_t run = s_w[w] + inc - sum;
+  for (uint32_t s = s0; s < s1; ++s) {
+    tile_base[s] = run;
+    run += (uint32_t)((segs[s].cnt + tile - 1) / tile);
+  }
+}
+
+static __global__ void fill_descs_kernel(const uint32_t* tile_base, const uint32_t* num_segs_ptr, const uint32_t* num_tiles_ptr, TileDesc* descs) {
+  const uint32_t ns = *num_segs_ptr, nt = *num_tiles_ptr;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = ns;           // largest s with tile_base[s] <= t
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (tile_base[mid] <= t) lo = mid; else hi = mid;
+    }
+    TileDesc td; td.seg = lo; td.tile_in_seg = t - tile_base[lo];
+    descs[t] = td;
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,24 @@
+// sort_api.h -- declarations shared by the per-type instantiation units (inst.cu) and the C ABI (api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct Twiddle;
+
+template <typename K, int VB>
+cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, void* v0, void* v1, int* selector,
+                          uint64_t n, const Twiddle& tw, int begin_bit, int end_bit, int allow_overwrite, cudaStream_t s);
+
+template <typename K, int VB>
+cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, void* vals_alt, const Twiddle& tw,
+                          void* d_ws, size_t* ws_bytes, cudaStream_t s, void** out_keys, void** out_vals);
+
+template <typename K, int VB>
+cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* kin, const void* vin, void* kout, void* vout,
+                                 uint64_t n, const Twiddle& tw, int bits, const uint32_t* d_splitters, int num_parts,
+                                 const uint64_t* d_local_counts, uint64_t* d_part_offsets, cudaStream_t s);
+
+}  // namespace b200

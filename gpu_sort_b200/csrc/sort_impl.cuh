@@ -1,0 +1,366 @@
+// sort_impl.cuh -- host orchestration (stream-ordered, no host<->device synchronisation, no allocation when the
+// caller supplies the temporary storage).
+//   lsb_sort_impl : stable LSD sort  = cub::DeviceRadixSort::{SortKeys,SortPairs}[Descending] call shape
+//                   (lsb/cub/cub/device/device_radix_sort.cuh:147-781; DispatchRadixSort::InvokePasses,
+//                   lsb/cub/cub/device/dispatch/dispatch_radix_sort.cuh:1050-1159), built as: one histogram read for all
+//                   digits -> one onesweep-style partition launch per digit.
+//   msb_sort_impl : MSB hybrid sort = rdxsrt_unstable_sort (msb/src/sort/gpu_radix_sort.h:187-507), built as:
+//                   per level [segment histograms -> classify -> partition -> next tile list], then ONE local-sort
+//                   launch over every bucket that fits on chip.  All scheduling stays on the device.
+#pragma once
+#include <algorithm>
+#include "hist.cuh"
+#include "local_sort.cuh"
+#include "msb_sched.cuh"
+#include "partition.cuh"
+
+namespace b200 {
+
+#define B200_CHECK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)
+
+inline int num_sms() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  return sms;
+}
+
+template <typename K, int VB>
+struct Cfg {
+  static constexpr int THREADS = 512;
+  static constexpr int IPT = 64 / sizeof(K);       // 16 x u32 / 8 x u64 per thread
+  static constexpr int TILE = THREADS * IPT;       // partition tile = local-sort capacity
+  static constexpr uint32_t MERGE_CAP = TILE / 4;  // runs of tiny neighbouring buckets are merged up to this size
+};
+
+// Persistent-grid size of a kernel: resident CTAs per SM x SMs (queried once per instantiation).
+template <typename KernelT>
+inline cudaError_t persistent_grid(KernelT kernel, int threads, size_t smem, int* grid) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  *grid = occ * num_sms();
+  return cudaSuccess;
+}
+
+template <typename K, int VB, bool ORDERED>
+inline cudaError_t launch_partition(const PartArgs& a, uint32_t tiles_hint, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  auto kernel = partition_kernel<K, VB, C::THREADS, C::IPT, ORDERED>;
+  constexpr size_t smem = sizeof(PartSmem<K, VB, C::THREADS, C::IPT, ORDERED>);
+  static int grid = 0;
+  if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
+  const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
+  kernel<<<g, C::THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename K, int VB>
+inline cudaError_t launch_local(const LocalArgs& a, uint32_t items_hint, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  auto kernel = local_sort_kernel<K, VB, C::THREADS, C::IPT>;
+  constexpr size_t smem = sizeof(LocalSmem<K, VB, C::THREADS, C::IPT>);
+  static int grid = 0;
+  if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
+  const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
+  kernel<<<g, C::THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// Tiny helper kernels --------------------------------------------------------------------------------------------
+static __global__ void single_item_kernel(LocalItem* item, uint32_t* num_items, uint32_t* ticket, uint32_t cnt, int nbits) {
+  LocalItem it; it.off = 0; it.cnt = cnt; it.nbits = (uint16_t)nbits; it.src = 0;
+  *item = it; *num_items = 1; *ticket = 0;
+}
+// Zeroes the rows of the per-level arrays that the level will actually use.
+static __global__ void level_prep_kernel(uint32_t* seg_hist, const uint32_t* num_segs_ptr, uint32_t* status, const uint32_t* num_tiles_ptr) {
+  const uint64_t nh = (uint64_t)*num_segs_ptr * RADIX / 4, ns = (uint64_t)*num_tiles_ptr * RADIX / 4;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (uint64_t i = t; i < nh; i += stride) reinterpret_cast<uint4*>(seg_hist)[i] = z;
+  for (uint64_t i = t; i < ns; i += stride) reinterpret_cast<uint4*>(status)[i] = z;
+}
+
+struct Carver {      // sub-allocates the caller's temporary storage, 256-byte aligned
+  char* base; size_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<char*>(p)) {}
+  template <typename T> T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return r;
+  }
+  size_t total() const { return (off + 255) & ~(size_t)255; }
+};
+
+// ===============================================================================================================
+// Stable LSB sort.
+// keys[0]/vals[0] = current (input), keys[1]/vals[1] = alternate.  *selector (out) = which one holds the result.
+// allow_overwrite = 0: the input buffers are left untouched and the result is delivered in the alternate buffers
+// (CUB's pointer overloads, device_radix_sort.cuh:147-179; needs a third buffer inside the temporary storage,
+// dispatch_radix_sort.cuh:1099-1104).
+// ===============================================================================================================
+template <typename K, int VB>
+cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, void* v0, void* v1, int* selector,
+                          uint64_t n, const Twiddle& tw, int begin_bit, int end_bit, int allow_overwrite, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  using V = typename ValType<VB>::type;
+  constexpr int KEY_BITS = sizeof(K) * 8;
+  if (begin_bit < 0) begin_bit = 0;
+  if (end_bit > KEY_BITS) end_bit = KEY_BITS;
+  const int passes = end_bit > begin_bit ? (end_bit - begin_bit + 7) / 8 : 0;
+  const uint64_t portion = (MAX_PORTION / C::TILE) * C::TILE;
+  const uint64_t max_tiles = (std::min<uint64_t>(n, portion) + C::TILE - 1) / C::TILE;
+  const bool need_third = !allow_overwrite && passes > 1 && n > (uint64_t)C::TILE;
+
+  Carver cv(d_temp);
+  unsigned long long* hist = cv.take<unsigned long long>((size_t)MAX_PASSES * RADIX);
+  uint64_t* pbins = cv.take<uint64_t>(2 * RADIX);
+  uint32_t* tick_status = cv.take<uint32_t>(64 + max_tiles * RADIX);     // [ticket | pad | status...], one memset clears both
+  LocalItem* one_item = cv.take<LocalItem>(1);
+  uint32_t* one_count = cv.take<uint32_t>(2);
+  K* k2 = need_third ? cv.take<K>(n) : nullptr;
+  V* v2 = (need_third && VB) ? cv.take<V>(n) : nullptr;
+  if (d_temp == nullptr) { *temp_bytes = std::max<size_t>(cv.total(), 256); return cudaSuccess; }
+  if (*temp_bytes < cv.total()) return cudaErrorInvalidValue;
+
+  if (selector) *selector = 0;
+  if (n == 0) return cudaSuccess;
+  if (passes == 0) {
+    if (!allow_overwrite) {
+      B200_CHECK(cudaMemcpyAsync(k1, k0, n * sizeof(K), cudaMemcpyDeviceToDevice, s));
+      if (VB) B200_CHECK(cudaMemcpyAsync(v1, v0, n * sizeof(V), cudaMemcpyDeviceToDevice, s));
+      if (selector) *selector = 1;
+    }
+    return cudaSuccess;
+  }
+
+  if (n <= (uint64_t)C::TILE) {     // single tile: one on-chip sort, result in the alternate buffer
+    single_item_kernel<<<1, 1, 0, s>>>(one_item, one_count, one_count + 1, (uint32_t)n, end_bit);
+    LocalArgs la{};
+    la.keys[0] = k0; la.keys[1] = k0; la.vals[0] = v0; la.vals[1] = v0;
+    la.keys_final = k1; la.vals_final = v1;
+    la.items = one_item; la.num_items_ptr = one_count; la.ticket = one_count + 1;
+    la.tw_in = 1; la.tw_out = 1; la.stable = 1; la.begin_bit = begin_bit; la.tw = tw;
+    B200_CHECK((launch_local<K, VB>(la, 1, s)));
+    if (selector) *selector = 1;
+    return cudaSuccess;
+  }
+
+  // ---- all digit histograms in one read, then digit starts
+  B200_CHECK(cudaMemsetAsync(hist, 0, (size_t)passes * RADIX * sizeof(unsigned long long), s));
+  {
+    HistAllArgs ha{};
+    ha.keys = k0; ha.n = n; ha.num_passes = passes; ha.begin_bit = begin_bit; ha.end_bit = end_bit;
+    ha.tw_in = 1; ha.tw = tw; ha.hist = hist;
+    const int grid = (int)std::min<uint64_t>((uint64_t)num_sms() * 4, (n + 4095) / 4096);
+    hist_all_kernel<K><<<grid, HIST_THREADS, 0, s>>>(ha);
+    scan_bins_kernel<<<passes, RADIX, 0, s>>>(hist, 0);
+  }
+
+  // ---- one partition launch per digit (per portion of < 2^30 keys)
+  const void* src_k = k0; const void* src_v = v0;
+  for (int p = 0; p < passes; ++p) {
+    void* dst_k; void* dst_v;
+    if (allow_overwrite) { dst_k = (p & 1) ? k0 : k1; dst_v = (p & 1) ? v0 : v1; }
+    else { const bool to_out = ((passes - 1 - p) & 1) == 0; dst_k = to_out ? k1 : (void*)k2; dst_v = to_out ? v1 : (void*)v2; }
+    const int shift = begin_bit + 8 * p;
+    const int nb = end_bit - shift < 8 ? end_bit - shift : 8;
+    int q = 0;
+    for (uint64_t base = 0; base < n; base += portion, ++q) {
+      const uint64_t pn = std::min<uint64_t>(portion, n - base);
+      const uint32_t tiles = (uint32_t)((pn + C::TILE - 1) / C::TILE);
+      B200_CHECK(cudaMemsetAsync(tick_status, 0, (64 + (size_t)tiles * RADIX) * sizeof(uint32_t), s));
+      PartArgs pa{};
+      pa.keys_in = src_k; pa.keys_out = dst_k; pa.vals_in = src_v; pa.vals_out = dst_v;
+      pa.segs = nullptr; pa.descs = nullptr; pa.num_tiles_ptr = nullptr;
+      pa.num_tiles = tiles; pa.base = base; pa.n = pn;
+      pa.bins = (q == 0) ? reinterpret_cast<const uint64_t*>(hist + (size_t)p * RADIX) : pbins + ((q - 1) & 1) * RADIX;
+      pa.bins_next = (base + pn < n) ? pbins + (q & 1) * RADIX : nullptr;
+      pa.status = tick_status + 64; pa.ticket = tick_status;
+      pa.shift = shift; pa.mask = (1u << nb) - 1u;
+      pa.tw_in = (p == 0); pa.tw_out = (p == passes - 1); pa.tw = tw;
+      B200_CHECK((launch_partition<K, VB, true>(pa, tiles, s)));
+    }
+    src_k = dst_k; src_v = dst_v;
+  }
+  if (selector) *selector = allow_overwrite ? (passes & 1) : 1;
+  return cudaSuccess;
+}
+
+// ===============================================================================================================
+// Unstable MSB hybrid sort.  Both buffer pairs are clobbered; *out_keys / *out_vals = the buffers holding the result
+// (the input buffers for 4- and 8-byte keys, like the reference: gpu_radix_sort.h:359-360).
+// ===============================================================================================================
+template <typename K, int VB>
+cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, void* vals_alt, const Twiddle& tw,
+                          void* d_ws, size_t* ws_bytes, cudaStream_t s, void** out_keys, void** out_vals) {
+  using C = Cfg<K, VB>;
+  constexpr int KEY_BITS = sizeof(K) * 8;
+  constexpr int LEVELS = sizeof(K);
+  if (out_keys) *out_keys = keys;
+  if (out_vals) *out_vals = vals;
+
+  if (n > MAX_PORTION) {     // beyond the 30-bit look-back range: the stable LSB path gives a valid result
+    int sel = 0;
+    cudaError_t e = lsb_sort_impl<K, VB>(d_ws, ws_bytes, keys, keys_alt, vals, vals_alt, &sel, n, tw, 0, KEY_BITS, 1, s);
+    if (d_ws && e == cudaSuccess && sel) { if (out_keys) *out_keys = keys_alt; if (out_vals) *out_vals = vals_alt; }
+    return e;
+  }
+
+  const uint32_t max_segs = (uint32_t)(n / C::TILE) + 2;
+  const uint32_t max_tiles = (uint32_t)(n / C::TILE) + max_segs + 1;
+  const uint32_t max_locals = (uint32_t)std::min<uint64_t>(4 * n / C::MERGE_CAP + 4ull * LEVELS * max_segs + 16, 0x7fffffffu);
+
+  Carver cv(d_ws);
+  MsbCounters* ctr = cv.take<MsbCounters>(1);
+  Seg* segs0 = cv.take<Seg>(max_segs);
+  Seg* segs1 = cv.take<Seg>(max_segs);
+  uint32_t* tile_base = cv.take<uint32_t>(max_segs + 1);
+  TileDesc* descs = cv.take<TileDesc>(max_tiles);
+  uint32_t* seg_hist = cv.take<uint32_t>((size_t)max_segs * RADIX);
+  uint64_t* bins = cv.take<uint64_t>((size_t)max_segs * RADIX);
+  uint32_t* status = cv.take<uint32_t>((size_t)max_tiles * RADIX);
+  LocalItem* locals = cv.take<LocalItem>(max_locals);
+  if (d_ws == nullptr) { *ws_bytes = std::max<size_t>(cv.total(), 256); return cudaSuccess; }
+  if (*ws_bytes < cv.total()) return cudaErrorInvalidValue;
+  if (n == 0) return cudaSuccess;
+
+  void* kbuf[2] = {keys, keys_alt};
+  void* vbuf[2] = {vals, vals_alt};
+  void* kfin = kbuf[LEVELS & 1];
+  void* vfin = vbuf[LEVELS & 1];
+  if (out_keys) *out_keys = kfin;
+  if (out_vals) *out_vals = vfin;
+  const int sms = num_sms();
+
+  if (n <= (uint64_t)C::TILE) {   // fits one CTA: a single on-chip sort, in place
+    single_item_kernel<<<1, 1, 0, s>>>(locals, &ctr->num_locals, &ctr->local_ticket, (uint32_t)n, KEY_BITS);
+    LocalArgs la{};
+    la.keys[0] = keys; la.keys[1] = keys; la.vals[0] = vals; la.vals[1] = vals;
+    la.keys_final = kfin; la.vals_final = vfin;
+    la.items = locals; la.num_items_ptr = &ctr->num_locals; la.ticket = &ctr->local_ticket;
+    la.tw_in = 1; la.tw_out = 1; la.stable = 0; la.begin_bit = 0; la.tw = tw;
+    if (kfin != keys) {   // odd level counts (not reachable for 4/8-byte keys): sort into the other buffer
+      la.keys_final = kfin; la.vals_final = vfin;
+    }
+    return launch_local<K, VB>(la, 1, s);
+  }
+
+  B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
+  msb_init_kernel<<<1, 32, 0, s>>>(segs0, ctr, n);
+  scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(segs0, &ctr->num_segs[0], tile_base, &ctr->num_tiles[0], max_tiles, &ctr->error, C::TILE);
+  fill_descs_kernel<<<sms * 2, 256, 0, s>>>(tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], descs);
+
+  for (int L = 0; L < LEVELS; ++L) {
+    const int shift = KEY_BITS - 8 * (L + 1);
+    Seg* cur = (L & 1) ? segs1 : segs0;
+    Seg* nxt = (L & 1) ? segs0 : segs1;
+    const void* in_k = kbuf[L & 1]; void* out_k = kbuf[(L + 1) & 1];
+    const void* in_v = vbuf[L & 1]; void* out_v = vbuf[(L + 1) & 1];
+
+    level_prep_kernel<<<sms * 2, 512, 0, s>>>(seg_hist, &ctr->num_segs[L], status, &ctr->num_tiles[L]);
+    SegHistArgs ha{};
+    ha.keys = in_k; ha.segs = cur; ha.descs = descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
+    ha.seg_hist = seg_hist; ha.tile = C::TILE; ha.shift = shift; ha.tw_in = (L == 0); ha.tw = tw;
+    seg_hist_kernel<K><<<sms * 4, HIST_THREADS, 0, s>>>(ha);
+
+    ClassifyArgs ca{};
+    ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = seg_hist; ca.bins = bins;
+    ca.next_segs = nxt; ca.num_next_ptr = &ctr->num_segs[L + 1]; ca.max_segs = max_segs;
+    ca.locals = locals; ca.num_locals_ptr = &ctr->num_locals; ca.max_locals = max_locals;
+    ca.error = &ctr->error; ca.shift = shift; ca.local_cap = C::TILE; ca.merge_cap = C::MERGE_CAP;
+    ca.out_buf = (uint32_t)((L + 1) & 1);
+    const int cgrid = (int)std::min<uint32_t>((max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
+    classify_kernel<<<L == 0 ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca);
+
+    PartArgs pa{};
+    pa.keys_in = in_k; pa.keys_out = out_k; pa.vals_in = in_v; pa.vals_out = out_v;
+    pa.segs = cur; pa.descs = descs; pa.num_tiles_ptr = &ctr->num_tiles[L];
+    pa.bins = bins; pa.bins_next = nullptr; pa.status = status; pa.ticket = &ctr->part_ticket[L];
+    pa.shift = shift; pa.mask = 0xFFu; pa.tw_in = (L == 0); pa.tw_out = (shift == 0); pa.tw = tw;
+    B200_CHECK((launch_partition<K, VB, false>(pa, max_tiles, s)));
+
+    if (L + 1 < LEVELS) {
+      scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(nxt, &ctr->num_segs[L + 1], tile_base, &ctr->num_tiles[L + 1], max_tiles, &ctr->error, C::TILE);
+      fill_descs_kernel<<<sms * 2, 256, 0, s>>>(tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], descs);
+    }
+  }
+
+  LocalArgs la{};
+  la.keys[0] = kbuf[0]; la.keys[1] = kbuf[1]; la.vals[0] = vbuf[0]; la.vals[1] = vbuf[1];
+  la.keys_final = kfin; la.vals_final = vfin;
+  la.items = locals; la.num_items_ptr = &ctr->num_locals; la.ticket = &ctr->local_ticket;
+  la.tw_in = 0; la.tw_out = 1; la.stable = 0; la.begin_bit = 0; la.tw = tw;
+  B200_CHECK((launch_local<K, VB>(la, max_locals, s)));
+  return cudaGetLastError();
+}
+
+// ===============================================================================================================
+// Multi-GPU send partition: stable split of (keys, values) into `num_parts` contiguous parts by key range.
+// The part of a key = number of splitters <= its top-`bits` bucket (transformed key).  d_local_counts is this
+// rank's own top-`bits` histogram (b200_msd_histogram), from which the part sizes follow without another read.
+// ===============================================================================================================
+static __global__ void __launch_bounds__(256) part_offsets_kernel(const uint64_t* counts, int nbuckets, const uint32_t* splitters, int num_parts,
+                                                                 uint64_t* part_offsets, uint64_t* bins) {
+  __shared__ unsigned long long sums[MAX_PARTS];
+  __shared__ uint32_t sp[MAX_PARTS];
+  if (threadIdx.x < MAX_PARTS) { sums[threadIdx.x] = 0; sp[threadIdx.x] = (int)threadIdx.x < num_parts - 1 ? splitters[threadIdx.x] : 0xFFFFFFFFu; }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nbuckets; b += blockDim.x) {
+    const uint64_t c = counts[b];
+    if (c) {
+      int d = 0;
+      for (int j = 0; j < num_parts - 1; ++j) d += ((uint32_t)b >= sp[j]) ? 1 : 0;
+      atomicAdd(&sums[d], (unsigned long long)c);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t run = 0;
+    for (int d = 0; d < RADIX; ++d) {
+      bins[d] = run;
+      if (d <= num_parts) part_offsets[d] = run;
+      if (d < num_parts) run += sums[d];
+    }
+  }
+}
+
+template <typename K, int VB>
+cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* kin, const void* vin, void* kout, void* vout,
+                                 uint64_t n, const Twiddle& tw, int bits, const uint32_t* d_splitters, int num_parts,
+                                 const uint64_t* d_local_counts, uint64_t* d_part_offsets, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  constexpr int KEY_BITS = sizeof(K) * 8;
+  if (num_parts < 1 || num_parts > MAX_PARTS || bits < 1 || bits > 16) return cudaErrorInvalidValue;
+  const uint64_t portion = (MAX_PORTION / C::TILE) * C::TILE;
+  const uint64_t max_tiles = (std::min<uint64_t>(n, portion) + C::TILE - 1) / C::TILE;
+  Carver cv(d_temp);
+  uint64_t* bins = cv.take<uint64_t>(RADIX);
+  uint64_t* pbins = cv.take<uint64_t>(2 * RADIX);
+  uint32_t* tick_status = cv.take<uint32_t>(64 + max_tiles * RADIX);
+  if (d_temp == nullptr) { *temp_bytes = std::max<size_t>(cv.total(), 256); return cudaSuccess; }
+  if (*temp_bytes < cv.total()) return cudaErrorInvalidValue;
+  part_offsets_kernel<<<1, 256, 0, s>>>(d_local_counts, 1 << bits, d_splitters, num_parts, d_part_offsets, bins);
+  int q = 0;
+  for (uint64_t base = 0; base < n; base += portion, ++q) {
+    const uint64_t pn = std::min<uint64_t>(portion, n - base);
+    const uint32_t tiles = (uint32_t)((pn + C::TILE - 1) / C::TILE);
+    B200_CHECK(cudaMemsetAsync(tick_status, 0, (64 + (size_t)tiles * RADIX) * sizeof(uint32_t), s));
+    PartArgs pa{};
+    pa.keys_in = kin; pa.keys_out = kout; pa.vals_in = vin; pa.vals_out = vout;
+    pa.num_tiles = tiles; pa.base = base; pa.n = pn;
+    pa.bins = (q == 0) ? bins : pbins + ((q - 1) & 1) * RADIX;
+    pa.bins_next = (base + pn < n) ? pbins + (q & 1) * RADIX : nullptr;
+    pa.status = tick_status + 64; pa.ticket = tick_status;
+    pa.shift = KEY_BITS - bits; pa.mask = (uint32_t)(num_parts - 1);
+    pa.tw_in = 1; pa.tw_out = 1; pa.tw = tw;
+    pa.splitters = d_splitters; pa.num_parts = num_parts;
+    B200_CHECK((launch_partition<K, VB, true>(pa, tiles, s)));
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace b200
