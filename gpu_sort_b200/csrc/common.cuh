@@ -115,9 +115,12 @@ struct Seg {            // a bucket that still needs a counting pass ("non-local
   uint64_t off;         // first key index
   uint64_t cnt;         // number of keys
 };
-struct TileDesc {       // one histogram / scatter tile of a segment
+struct TileDesc {       // one histogram / scatter tile of a segment, self-contained so a tile costs one load
+  uint64_t off;         // first key index of the tile
+  uint32_t cnt;         // keys in the tile
   uint32_t seg;         // index into the level's Seg list
   uint32_t tile_in_seg;
+  uint32_t pad;
 };
 struct LocalItem {      // a bucket (or merged run of tiny buckets) that is finished on-chip
   uint64_t off;         // first key index

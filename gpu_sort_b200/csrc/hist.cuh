@@ -110,11 +110,8 @@ __global__ void __launch_bounds__(HIST_THREADS) seg_hist_kernel(const __grid_con
       __syncthreads();
       cur_seg = td.seg;
     }
-    const Seg sg = a.segs[td.seg];
-    const uint64_t rel = (uint64_t)td.tile_in_seg * a.tile;
-    const uint64_t rem = sg.cnt - rel;
-    const uint32_t cnt = rem < (uint64_t)a.tile ? (uint32_t)rem : (uint32_t)a.tile;
-    const K* p = keys + sg.off + rel;
+    const uint32_t cnt = td.cnt;
+    const K* p = keys + td.off;
     for (uint32_t i = threadIdx.x; i < cnt; i += HIST_THREADS) {
       K k = p[i];
       if (a.tw_in) k = twiddle_in<K>(k, a.tw);

@@ -38,7 +38,7 @@ struct LocalSmem {
 };
 
 template <typename K, int VB, int THREADS, int IPT>
-__global__ void __launch_bounds__(THREADS) local_sort_kernel(const __grid_constant__ LocalArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) local_sort_kernel(const __grid_constant__ LocalArgs a) {
   using V = typename ValType<VB>::type;
   using SM = LocalSmem<K, VB, THREADS, IPT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,13 +98,12 @@ __global__ void __launch_bounds__(THREADS) local_sort_kernel(const __grid_consta
       const int shift = lo + 8 * p;
       const int nb = hi - shift < 8 ? hi - shift : 8;
       const uint32_t mask = (1u << nb) - 1u;
-      uint32_t dg[IPT], pos[IPT], t0, t1;
-#pragma unroll
-      for (int j = 0; j < IPT; ++j) dg[j] = digit_of<K>(key[j], shift, mask);
+      uint32_t pos[IPT], t0, t1;
+      auto dfn = [&](K k) { return digit_of<K>(k, shift, mask); };
       if (p == 0 && !first_ordered)
-        tile_positions<THREADS, IPT, false>(dg, valid, rows, 0u, mask, pos, sm.rank.unordered, t0, t1);
+        tile_positions<THREADS, IPT, false>(key, dfn, valid, rows, 0u, mask, pos, sm.rank.unordered, t0, t1);
       else
-        tile_positions<THREADS, IPT, true>(dg, valid, rows, (uint32_t)rows * THREADS - cnt, mask, pos, sm.rank.ordered, t0, t1);
+        tile_positions<THREADS, IPT, true>(key, dfn, valid, rows, (uint32_t)rows * THREADS - cnt, mask, pos, sm.rank.ordered, t0, t1);
 #pragma unroll
       for (int j = 0; j < IPT; ++j)
         if ((valid >> j) & 1u) {

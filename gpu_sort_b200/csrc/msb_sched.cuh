@@ -164,7 +164,8 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const S
   }
 }
 
-static __global__ void fill_descs_kernel(const uint32_t* tile_base, const uint32_t* num_segs_ptr, const uint32_t* num_tiles_ptr, TileDesc* descs) {
+static __global__ void fill_descs_kernel(const Seg* segs, const uint32_t* tile_base, const uint32_t* num_segs_ptr, const uint32_t* num_tiles_ptr,
+                                         TileDesc* descs, int tile) {
   const uint32_t ns = *num_segs_ptr, nt = *num_tiles_ptr;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = ns;           // largest s with tile_base[s] <= t
@@ -172,7 +173,11 @@ static __global__ void fill_descs_kernel(const uint32_t* tile_base, const uint32
       const uint32_t mid = (lo + hi) >> 1;
       if (tile_base[mid] <= t) lo = mid; else hi = mid;
     }
-    TileDesc td; td.seg = lo; td.tile_in_seg = t - tile_base[lo];
+    const Seg sg = segs[lo];
+    TileDesc td; td.seg = lo; td.tile_in_seg = t - tile_base[lo]; td.pad = 0;
+    const uint64_t rel = (uint64_t)td.tile_in_seg * tile;
+    td.off = sg.off + rel;
+    td.cnt = (uint32_t)(sg.cnt - rel < (uint64_t)tile ? sg.cnt - rel : (uint64_t)tile);
     descs[t] = td;
   }
 }

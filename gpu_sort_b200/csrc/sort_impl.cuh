@@ -175,7 +175,7 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
       B200_CHECK(cudaMemsetAsync(tick_status, 0, (64 + (size_t)tiles * RADIX) * sizeof(uint32_t), s));
       PartArgs pa{};
       pa.keys_in = src_k; pa.keys_out = dst_k; pa.vals_in = src_v; pa.vals_out = dst_v;
-      pa.segs = nullptr; pa.descs = nullptr; pa.num_tiles_ptr = nullptr;
+      pa.descs = nullptr; pa.num_tiles_ptr = nullptr;
       pa.num_tiles = tiles; pa.base = base; pa.n = pn;
       pa.bins = (q == 0) ? reinterpret_cast<const uint64_t*>(hist + (size_t)p * RADIX) : pbins + ((q - 1) & 1) * RADIX;
       pa.bins_next = (base + pn < n) ? pbins + (q & 1) * RADIX : nullptr;
@@ -252,7 +252,7 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
   B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
   msb_init_kernel<<<1, 32, 0, s>>>(segs0, ctr, n);
   scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(segs0, &ctr->num_segs[0], tile_base, &ctr->num_tiles[0], max_tiles, &ctr->error, C::TILE);
-  fill_descs_kernel<<<sms * 2, 256, 0, s>>>(tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], descs);
+  fill_descs_kernel<<<sms * 2, 256, 0, s>>>(segs0, tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], descs, C::TILE);
 
   for (int L = 0; L < LEVELS; ++L) {
     const int shift = KEY_BITS - 8 * (L + 1);
@@ -278,14 +278,14 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
 
     PartArgs pa{};
     pa.keys_in = in_k; pa.keys_out = out_k; pa.vals_in = in_v; pa.vals_out = out_v;
-    pa.segs = cur; pa.descs = descs; pa.num_tiles_ptr = &ctr->num_tiles[L];
+    pa.descs = descs; pa.num_tiles_ptr = &ctr->num_tiles[L];
     pa.bins = bins; pa.bins_next = nullptr; pa.status = status; pa.ticket = &ctr->part_ticket[L];
     pa.shift = shift; pa.mask = 0xFFu; pa.tw_in = (L == 0); pa.tw_out = (shift == 0); pa.tw = tw;
     B200_CHECK((launch_partition<K, VB, false>(pa, max_tiles, s)));
 
     if (L + 1 < LEVELS) {
       scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(nxt, &ctr->num_segs[L + 1], tile_base, &ctr->num_tiles[L + 1], max_tiles, &ctr->error, C::TILE);
-      fill_descs_kernel<<<sms * 2, 256, 0, s>>>(tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], descs);
+      fill_descs_kernel<<<sms * 2, 256, 0, s>>>(nxt, tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], descs, C::TILE);
     }
   }
 
