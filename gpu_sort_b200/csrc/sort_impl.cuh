@@ -26,10 +26,15 @@ inline int num_sms() {
 
 template <typename K, int VB>
 struct Cfg {
+  // partition tile: 512 threads x (16 x u32 | 8 x u64) keys, two CTAs per SM
   static constexpr int THREADS = 512;
-  static constexpr int IPT = 64 / sizeof(K);       // 16 x u32 / 8 x u64 per thread
-  static constexpr int TILE = THREADS * IPT;       // partition tile = local-sort capacity
-  static constexpr uint32_t MERGE_CAP = TILE / 4;  // runs of tiny neighbouring buckets are merged up to this size
+  static constexpr int IPT = (sizeof(K) == 4 && VB == 8) ? 8 : 64 / sizeof(K);
+  static constexpr int TILE = THREADS * IPT;
+  // local sort: capacity = the largest bucket that is finished on chip (everything larger gets another level)
+  static constexpr int LOCAL_THREADS = sizeof(K) == 4 ? 384 : (VB == 0 ? 768 : 512);
+  static constexpr int LOCAL_IPT = sizeof(K) == 4 ? (VB == 8 ? 8 : 16) : (VB == 0 ? 12 : 8);
+  static constexpr int LOCAL_CAP = LOCAL_THREADS * LOCAL_IPT;
+  static constexpr uint32_t MERGE_CAP = LOCAL_CAP / 4;  // runs of tiny neighbouring buckets are merged up to this size
 };
 
 // Persistent-grid size of a kernel: resident CTAs per SM x SMs (queried once per instantiation).
@@ -50,6 +55,7 @@ inline cudaError_t launch_partition(const PartArgs& a, uint32_t tiles_hint, cuda
   using C = Cfg<K, VB>;
   auto kernel = partition_kernel<K, VB, C::THREADS, C::IPT, ORDERED>;
   constexpr size_t smem = sizeof(PartSmem<K, VB, C::THREADS, C::IPT, ORDERED>);
+  static_assert(smem <= 227 * 1024, "partition tile exceeds the 227 KB shared-memory limit");
   static int grid = 0;
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
@@ -60,12 +66,13 @@ inline cudaError_t launch_partition(const PartArgs& a, uint32_t tiles_hint, cuda
 template <typename K, int VB>
 inline cudaError_t launch_local(const LocalArgs& a, uint32_t items_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
-  auto kernel = local_sort_kernel<K, VB, C::THREADS, C::IPT>;
-  constexpr size_t smem = sizeof(LocalSmem<K, VB, C::THREADS, C::IPT>);
+  auto kernel = local_sort_kernel<K, VB, C::LOCAL_THREADS, C::LOCAL_IPT>;
+  constexpr size_t smem = sizeof(LocalSmem<K, VB, C::LOCAL_THREADS, C::LOCAL_IPT>);
+  static_assert(smem <= 227 * 1024, "local sort exceeds the 227 KB shared-memory limit");
   static int grid = 0;
-  if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
+  if (!grid) B200_CHECK(persistent_grid(kernel, C::LOCAL_THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
-  kernel<<<g, C::THREADS, smem, s>>>(a);
+  kernel<<<g, C::LOCAL_THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -113,7 +120,7 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
   const int passes = end_bit > begin_bit ? (end_bit - begin_bit + 7) / 8 : 0;
   const uint64_t portion = (MAX_PORTION / C::TILE) * C::TILE;
   const uint64_t max_tiles = (std::min<uint64_t>(n, portion) + C::TILE - 1) / C::TILE;
-  const bool need_third = !allow_overwrite && passes > 1 && n > (uint64_t)C::TILE;
+  const bool need_third = !allow_overwrite && passes > 1 && n > (uint64_t)C::LOCAL_CAP;
 
   Carver cv(d_temp);
   unsigned long long* hist = cv.take<unsigned long long>((size_t)MAX_PASSES * RADIX);
@@ -137,12 +144,12 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     return cudaSuccess;
   }
 
-  if (n <= (uint64_t)C::TILE) {     // single tile: one on-chip sort, result in the alternate buffer
+  if (n <= (uint64_t)C::LOCAL_CAP) {     // single tile: one on-chip sort, result in the alternate buffer
     single_item_kernel<<<1, 1, 0, s>>>(one_item, one_count, one_count + 1, (uint32_t)n, end_bit);
     LocalArgs la{};
     la.keys[0] = k0; la.keys[1] = k0; la.vals[0] = v0; la.vals[1] = v0;
     la.keys_final = k1; la.vals_final = v1;
-    la.items = one_item; la.num_items_ptr = one_count; la.ticket = one_count + 1;
+    la.items = one_item; la.num_items_ptr = one_count;
     la.tw_in = 1; la.tw_out = 1; la.stable = 1; la.begin_bit = begin_bit; la.tw = tw;
     B200_CHECK((launch_local<K, VB>(la, 1, s)));
     if (selector) *selector = 1;
@@ -210,7 +217,7 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
     return e;
   }
 
-  const uint32_t max_segs = (uint32_t)(n / C::TILE) + 2;
+  const uint32_t max_segs = (uint32_t)(n / C::LOCAL_CAP) + 2;
   const uint32_t max_tiles = (uint32_t)(n / C::TILE) + max_segs + 1;
   const uint32_t max_locals = (uint32_t)std::min<uint64_t>(4 * n / C::MERGE_CAP + 4ull * LEVELS * max_segs + 16, 0x7fffffffu);
 
@@ -236,12 +243,12 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
   if (out_vals) *out_vals = vfin;
   const int sms = num_sms();
 
-  if (n <= (uint64_t)C::TILE) {   // fits one CTA: a single on-chip sort, in place
+  if (n <= (uint64_t)C::LOCAL_CAP) {   // fits one CTA: a single on-chip sort, in place
     single_item_kernel<<<1, 1, 0, s>>>(locals, &ctr->num_locals, &ctr->local_ticket, (uint32_t)n, KEY_BITS);
     LocalArgs la{};
     la.keys[0] = keys; la.keys[1] = keys; la.vals[0] = vals; la.vals[1] = vals;
     la.keys_final = kfin; la.vals_final = vfin;
-    la.items = locals; la.num_items_ptr = &ctr->num_locals; la.ticket = &ctr->local_ticket;
+    la.items = locals; la.num_items_ptr = &ctr->num_locals;
     la.tw_in = 1; la.tw_out = 1; la.stable = 0; la.begin_bit = 0; la.tw = tw;
     if (kfin != keys) {   // odd level counts (not reachable for 4/8-byte keys): sort into the other buffer
       la.keys_final = kfin; la.vals_final = vfin;
@@ -271,7 +278,7 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
     ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = seg_hist; ca.bins = bins;
     ca.next_segs = nxt; ca.num_next_ptr = &ctr->num_segs[L + 1]; ca.max_segs = max_segs;
     ca.locals = locals; ca.num_locals_ptr = &ctr->num_locals; ca.max_locals = max_locals;
-    ca.error = &ctr->error; ca.shift = shift; ca.local_cap = C::TILE; ca.merge_cap = C::MERGE_CAP;
+    ca.error = &ctr->error; ca.shift = shift; ca.local_cap = C::LOCAL_CAP; ca.merge_cap = C::MERGE_CAP;
     ca.out_buf = (uint32_t)((L + 1) & 1);
     const int cgrid = (int)std::min<uint32_t>((max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
     classify_kernel<<<L == 0 ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca);
@@ -292,7 +299,7 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
   LocalArgs la{};
   la.keys[0] = kbuf[0]; la.keys[1] = kbuf[1]; la.vals[0] = vbuf[0]; la.vals[1] = vbuf[1];
   la.keys_final = kfin; la.vals_final = vfin;
-  la.items = locals; la.num_items_ptr = &ctr->num_locals; la.ticket = &ctr->local_ticket;
+  la.items = locals; la.num_items_ptr = &ctr->num_locals;
   la.tw_in = 0; la.tw_out = 1; la.stable = 0; la.begin_bit = 0; la.tw = tw;
   B200_CHECK((launch_local<K, VB>(la, max_locals, s)));
   return cudaGetLastError();
