@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark of the B200-native radix sort (see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3|cfg4|cfg5] [--logn L]
+
+Metric (BASELINE.json): Gkeys/s.  A step = ONE sort of one batch of synthetic keys.
+  N = 1 (default) : BASELINE config 2 -- 2^28 uniform uint32 keys, keys-only, MSB hybrid sort (rdxsrt_unstable_sort call
+                    shape) through the C ABI.  `value` times the sort call alone with the keys resident in HBM (CUDA events
+                    around every step, the input is restored by a D2D copy between steps -- the reference's own protocol,
+                    lsb/sort.cu:141-146); `e2e` times the host-pointer entry point (b200_msb_sort_host: H2D + sort + D2H).
+  N > 1 (torchrun): weak scaling -- every rank holds 2^28 keys of ONE global array of N*2^28 keys, sorted with the multi-GPU
+                    path (histogram all-reduce, splitters, key all-to-all over NVLink, local sort): gpu_sort_b200/dist.py.
+  --impl reference: the UNMODIFIED reference (oracle/_ref/libref_msb.so, compiled from /root/reference) on the same
+                    workload on the same GPU; if that library is missing, the CPU port (oracle/) on a bounded sample.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (log2 n, key bits, value bytes, path, dist, param, algorithmic full sweeps S, description)
+    "cfg1": (24, 32, 0, "msb", "uniform", 0, 3, "2^24 uniform uint32 keys, keys-only, MSB hybrid"),
+    "cfg2": (28, 32, 0, "msb", "uniform", 0, 3, "2^28 uniform uint32 keys, keys-only, MSB hybrid radix sort"),
+    "cfg3": (28, 32, 4, "lsb", "uniform", 0, 4, "2^28 uint32 key + uint32 value pairs, stable LSB sort"),
+    "cfg4": (29, 64, 0, "msb", "zipf_hash", 0, 3, "2^29 uint64 keys, Zipf-skewed, MSB hybrid"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv"); os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_baseline(n_sample=1 << 26):
+    """std::sort on one core and __gnu_parallel::sort on all cores (oracle/libcpusort.so) over a bounded sample of the
+    workload's keys -- a reported baseline, not the target."""
+    so = os.path.join(ROOT, "oracle", "libcpusort.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libcpusort.so"], stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(so)
+    lib.cpu_sort_u32.restype = ctypes.c_double
+    lib.cpu_sort_u32.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int]
+    lib.cpu_sort_max_threads.restype = ctypes.c_int
+    from tests import oracle_lib
+    keys = oracle_lib.load().gen_keys(n_sample, 32, seed=0, dist="uniform")
+    cores = lib.cpu_sort_max_threads()
+    a = keys.copy()
+    t_par = lib.cpu_sort_u32(a.ctypes.data, a.size, 0)
+    n1 = n_sample >> 2
+    b = keys[:n1].copy()
+    t_one = lib.cpu_sort_u32(b.ctypes.data, b.size, 1)
+    assert np.all(a[1:] >= a[:-1])
+    return {"value": round(n_sample / t_par / 1e9, 4), "unit": "Gkeys/s", "cores": cores, "kind": "port",
+            "sample": f"__gnu_parallel::sort of 2^{int(np.log2(n_sample))} uniform u32 keys (same generator/seed as the workload) on {cores} threads",
+            "std_sort_1core_gkeys_s": round(n1 / t_one / 1e9, 4), "std_sort_sample": f"2^{int(np.log2(n1))} keys"}
+
+
+def time_steps(step_fn, restore_fn, steps, warmup, barrier):
+    """W untimed warm-ups, then K steps; each step = restore (untimed) + sort between two CUDA events on the current stream."""
+    for _ in range(warmup):
+        restore_fn(); step_fn()
+    torch.cuda.synchronize(); barrier()
+    evs = []
+    wall0 = time.time()
+    for _ in range(steps):
+        restore_fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step_fn(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize(); barrier()
+    wall = time.time() - wall0
+    ms = [a.elapsed_time(b) for a, b in evs]
+    return ms, wall
+
+
+def run_ours_single(args, wl):
+    import gpu_sort_b200 as gs
+    logn, kbits, vb, path, dist, param, S, desc = wl
+    if args.logn:
+        logn = args.logn
+    n = 1 << logn
+    kt = gs.KEY_U32 if kbits == 32 else gs.KEY_U64
+    kdt = torch.int32 if kbits == 32 else torch.int64
+    vdt = torch.int32 if vb == 4 else torch.int64
+    src = torch.empty(n, dtype=kdt, device="cuda"); gs.generate_keys(src, seed=0, dist=dist, param=param)
+    vsrc = gs.iota(torch.empty(n, dtype=vdt, device="cuda")) if vb else None
+    k0, k1 = torch.empty_like(src), torch.empty_like(src)
+    v0 = torch.empty_like(vsrc) if vb else None; v1 = torch.empty_like(vsrc) if vb else None
+    digest_in = gs.check(src, vsrc, key_type=kt)[:2]
+    if path == "lsb":
+        tb = gs.DeviceRadixSort._run(None, gs.DoubleBuffer(k0, k1), gs.DoubleBuffer(v0, v1) if vb else None, n, 0, None, False, None, kt)
+    else:
+        tb = gs.rdxsrt_workspace_bytes(n, kt, vb)
+    temp = torch.empty(tb, dtype=torch.uint8, device="cuda")
+    res = {}
+
+    def restore():
+        k0.copy_(src)
+        if vb:
+            v0.copy_(vsrc)
+
+    def step():
+        if path == "lsb":
+            dk = gs.DoubleBuffer(k0, k1); dv = gs.DoubleBuffer(v0, v1) if vb else None
+            gs.DeviceRadixSort._run(temp, dk, dv, n, 0, None, False, None, kt)
+            res["k"], res["v"] = dk.Current(), (dv.Current() if vb else None)
+        else:
+            r = gs.rdxsrt_unstable_sort(k0, v0 if vb else None, n, k1, v1 if vb else None, workspace=temp, key_type=kt)
+            res["k"], res["v"] = r.sorted_keys, r.sorted_values
+
+    clocks = ClockSampler(torch.cuda.current_device()); clocks.start()
+    ms, wall = time_steps(step, restore, args.steps, args.warmup, lambda: None)
+    clk = clocks.stop()
+    s, x, bad, vbad = gs.check(res["k"], res["v"], key_type=kt)
+    ok = bad == 0 and (s, x) == digest_in and (path != "lsb" or not vb or vbad == 0)
+
+    # ---- per-kernel durations: the same steps again with every launch bracketed by CUDA events (b200_prof_*)
+    gs.prof_enable(True)
+    for _ in range(args.steps):
+        restore(); step()
+    torch.cuda.synchronize()
+    prof = gs.prof_report(); gs.prof_enable(False)
+    launches_per_step = sum(c for c, _ in prof.values()) / args.steps
+    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    dom_name, (dom_cnt, dom_ms) = dom
+    kbytes, vbytes = kbits // 8, vb
+    sweep_bytes = 2 * n * (kbytes + vbytes)
+    # algorithmic bytes of the dominant kernel per step (DESIGN.md "Kernels"): the scatter kernels move every key once per
+    # sweep they run (read + write); the on-chip local sort likewise (one read + one write of every key).
+    if dom_name in ("partition_msb", "partition_lsb"):
+        sweeps = (S - 1) if path == "msb" else S
+    else:
+        sweeps = 1
+    dom_bytes = sweeps * sweep_bytes
+    dom_ms_per_step = dom_ms / args.steps
+    peak, peak_src = peaks()
+    achieved = dom_bytes / (dom_ms_per_step * 1e-3) / 1e9
+    med = float(np.median(ms)); mean = float(np.mean(ms))
+    whole_bytes = n * kbytes + S * sweep_bytes
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": round(dom_ms_per_step, 4),
+                "kernel_launches_per_step": dom_cnt / args.steps, "kernel_share_of_step": round(dom_ms_per_step / (sum(v for _, v in prof.values()) / args.steps), 3),
+                "whole_sort": {"algorithmic_bytes": whole_bytes, "bytes_per_key": whole_bytes / n, "achieved_gbs": round(whole_bytes / (mean * 1e-3) / 1e9, 1),
+                               "frac": round(whole_bytes / (mean * 1e-3) / 1e9 / peak, 4)},
+                "kernels_ms_per_step": {k: round(v / args.steps, 4) for k, (c, v) in prof.items()}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(dom_name, {}).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- end to end through the host-pointer entry point (pinned host buffers; H2D + sort + D2H inside the timed region)
+    e2e = None
+    if path == "msb" and not args.no_e2e:
+        hk = torch.empty(n, dtype=kdt).pin_memory(); hk.copy_(src)
+        ho = torch.empty(n, dtype=kdt).pin_memory()
+        hv = hvo = None
+        if vb:
+            hv = torch.empty(n, dtype=vdt).pin_memory(); hv.copy_(vsrc); hvo = torch.empty(n, dtype=vdt).pin_memory()
+        e2e_steps = max(3, min(args.steps, 10))
+        call = lambda: gs._check(gs.lib.b200_msb_sort_host(hk.data_ptr(), hv.data_ptr() if vb else None, n, ho.data_ptr(), hvo.data_ptr() if vb else None, kt, vb), "b200_msb_sort_host")
+        call(); call()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            call()                       # synchronous on return, like the reference's wrapper (gpu_radix_sort.h:510-541)
+        dt = (time.perf_counter() - t0) / e2e_steps
+        a = ho.numpy().view(np.uint32 if kbits == 32 else np.uint64)
+        ok = ok and bool(np.all(a[1:] >= a[:-1]))
+        e2e = {"value": round(n / dt / 1e9, 3), "unit": "Gkeys/s", "h2d_bytes_per_step": n * (kbytes + vbytes), "d2h_bytes_per_step": n * (kbytes + vbytes),
+               "ms_per_step": round(dt * 1e3, 3), "steps": e2e_steps, "entry": "b200_msb_sort_host (pinned host buffers)"}
+
+    line = {"metric": "Gkeys/s", "value": round(n / (mean * 1e-3) / 1e9, 3), "unit": "Gkeys/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(mean, 4), "ms_median": round(med, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32" if kbits == 32 else "u64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "n": n, "path": path, "key_bits": kbits, "value_bytes": vb, "dist": dist,
+                       "l2": "inputs (>= 1 GiB) larger than the 126 MB L2; input restored by an untimed D2D copy between steps",
+                       "timing": "CUDA events around each sort call on the launching stream, summed over the K steps"},
+            "roofline": roofline, "clocks": clk, "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
+            "verified": ok, "wall_s_timed_region": round(wall, 3)}
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline()
+    return line
+
+
+def run_ours_multi(args, rank, world):
+    """Weak scaling: N x 2^logn keys of one global array (keys-only u32, uniform); gpu_sort_b200/dist.py."""
+    import torch.distributed as dist
+    import gpu_sort_b200 as gs
+    from gpu_sort_b200 import dist as gd
+    logn = args.logn or 28
+    n_l = 1 << logn
+    total = n_l * world
+    pairs = args.workload == "cfg5"
+    src = torch.empty(n_l, dtype=torch.int32, device="cuda")
+    gs.generate_keys(src, seed=0, dist="uniform", start=rank * n_l, total=total)
+    vsrc = gs.iota(torch.empty(n_l, dtype=torch.int32, device="cuda"), start=rank * n_l) if pairs else None
+    keys = torch.empty_like(src); vals = torch.empty_like(vsrc) if pairs else None
+    din = gs.check(src, vsrc, key_type=gs.KEY_U32)[0]
+    res = {}
+
+    def restore():
+        keys.copy_(src)
+        if pairs:
+            vals.copy_(vsrc)
+
+    def step():
+        res["k"], res["v"], res["info"] = gd.distributed_sort(keys, vals, key_type=gs.KEY_U32, stable=pairs)
+
+    clocks = ClockSampler(torch.cuda.current_device()); clocks.start()
+    ms, wall = time_steps(step, restore, args.steps, args.warmup, dist.barrier)
+    clk = clocks.stop()
+    t = torch.tensor([float(np.sum(ms))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                       # max over ranks of the device-timed K steps
+    total_ms = float(t.item())
+    # validation: per-rank sortedness, boundary order between neighbouring ranks, global multiset digest
+    s, x, bad, vbad = gs.check(res["k"], res["v"], key_type=gs.KEY_U32)
+    mine = res["k"].view(torch.int32)
+    lo = int(mine[0].item()) & 0xFFFFFFFF if mine.numel() else None
+    hi = int(mine[-1].item()) & 0xFFFFFFFF if mine.numel() else None
+    rec = {"sum": s, "bad": bad, "vbad": vbad if pairs else 0, "n": mine.numel(), "lo": lo, "hi": hi, "din": din}
+    recs = [None] * world
+    dist.all_gather_object(recs, rec)
+    ok = all(r["bad"] == 0 and r["vbad"] == 0 for r in recs) and sum(r["n"] for r in recs) == total
+    nz = [r for r in recs if r["n"]]
+    ok = ok and all(nz[i]["hi"] <= nz[i + 1]["lo"] for i in range(len(nz) - 1))
+    ok = ok and sum(r["sum"] for r in recs) % (1 << 64) == sum(r["din"] for r in recs) % (1 << 64)
+    if rank != 0:
+        return None
+    mean = total_ms / args.steps
+    kb = 8 if pairs else 4
+    return {"metric": "Gkeys/s", "value": round(total / (mean * 1e-3) / 1e9, 3), "unit": "Gkeys/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(mean, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"{'cfg5-style pairs' if pairs else 'cfg2 weak-scaled'}: 2^{logn} uniform uint32 {'key+value pairs' if pairs else 'keys'} per GPU, one global array of {world}x2^{logn}, "
+                                   "histogram all-reduce + key-range all-to-all over NVLink + local sort", "n_total": total, "n_per_gpu": n_l, "value_bytes": 4 if pairs else 0,
+                       "l2": "inputs larger than L2; restored by an untimed D2D copy between steps", "timing": "CUDA events per step on each rank; max over ranks of the K-step sum"},
+            "exchange": {"imbalance": round(res["info"]["imbalance"], 4), "nvlink_bytes_out_per_gpu": int(n_l * kb * (world - 1) / world)},
+            "clocks": clk, "gpu_launches": None, "verified": bool(ok), "wall_s_timed_region": round(wall, 3)}
+
+
+def run_reference(args, wl):
+    """The unmodified reference's GPU build (oracle/_ref) on the same workload; CPU port if it is not there."""
+    logn, kbits, vb, path, dist, param, S, desc = wl
+    if args.logn:
+        logn = args.logn
+    n = 1 << logn
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_msb.so" if path == "msb" else "libref_lsb.so")
+    if not (os.path.exists(so) and torch.cuda.is_available()):
+        cb = cpu_baseline()
+        return {"impl": "reference", "metric": "Gkeys/s", "value": cb["value"], "unit": "Gkeys/s", "n_gpus": 1, "steps": 1, "warmup": 0, "higher_is_better": True,
+                "config": {"workload": f"{args.workload}: {desc} (bounded CPU sample)"}, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    import gpu_sort_b200 as gs           # only for the shared input generator + result check (b200_util_*)
+    kt = gs.KEY_U32 if kbits == 32 else gs.KEY_U64
+    kdt = torch.int32 if kbits == 32 else torch.int64
+    vdt = torch.int32 if vb == 4 else torch.int64
+    src = torch.empty(n, dtype=kdt, device="cuda"); gs.generate_keys(src, seed=0, dist=dist, param=param)
+    vsrc = gs.iota(torch.empty(n, dtype=vdt, device="cuda")) if vb else None
+    k0, k1 = torch.empty_like(src), torch.empty_like(src)
+    v0 = torch.empty_like(vsrc) if vb else None; v1 = torch.empty_like(vsrc) if vb else None
+    P = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+    lib = ctypes.CDLL(so)
+    res = {}
+
+    def restore():
+        k0.copy_(src)
+        if vb:
+            v0.copy_(vsrc)
+
+    if path == "msb":
+        lib.ref_msb_sort_device.restype = ctypes.c_int
+        ok_, ov_ = ctypes.c_void_p(0), ctypes.c_void_p(0)
+
+        def step():      # rdxsrt_unstable_sort as shipped: allocates its data manager + streams inside the call, synchronous on return
+            lib.ref_msb_sort_device(P(k0), P(v0), ctypes.c_ulonglong(n), P(k1), P(v1), ctypes.c_int(kbits), ctypes.c_int(vb), ctypes.byref(ok_), ctypes.byref(ov_))
+            res["k"] = k0 if ok_.value == k0.data_ptr() else k1
+            res["v"] = (v0 if ov_.value == v0.data_ptr() else v1) if vb else None
+        api = "rdxsrt_unstable_sort (msb/src/sort/gpu_radix_sort.h:187-507), unmodified, sm_100a build"
+    else:
+        lib.ref_lsb_cub_sort.restype = ctypes.c_int
+        tb = ctypes.c_size_t(0); sel = ctypes.c_int(0)
+        rkt = 0 if kbits == 32 else 1
+        lib.ref_lsb_cub_sort(None, ctypes.byref(tb), P(k0), P(k1), P(v0), P(v1), ctypes.c_int(n), rkt, vb, 0, 0, kbits, ctypes.byref(sel))
+        temp = torch.empty(max(tb.value, 1), dtype=torch.uint8, device="cuda")
+
+        def step():
+            lib.ref_lsb_cub_sort(P(temp), ctypes.byref(tb), P(k0), P(k1), P(v0), P(v1), ctypes.c_int(n), rkt, vb, 0, 0, kbits, ctypes.byref(sel))
+            res["k"] = k1 if sel.value else k0
+            res["v"] = (v1 if sel.value else v0) if vb else None
+        api = "cub::DeviceRadixSort call shape of lsb/sort.cu:25-76 (toolkit CUB 2.8.2; vendored 1.6.4 cannot assemble for sm_100)"
+
+    clocks = ClockSampler(torch.cuda.current_device()); clocks.start()
+    devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)       # the reference prints its thresholds on first use
+    try:
+        ms, wall = time_steps(step, restore, args.steps, args.warmup, lambda: None)
+    finally:
+        os.dup2(saved, 1); os.close(devnull)
+    clk = clocks.stop()
+    s, x, bad, _ = gs.check(res["k"], res["v"], key_type=kt)
+    mean = float(np.mean(ms))
+    line = {"impl": "reference", "metric": "Gkeys/s", "value": round(n / (mean * 1e-3) / 1e9, 3), "unit": "Gkeys/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(mean, 4), "ms_median": round(float(np.median(ms)), 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32" if kbits == 32 else "u64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "n": n, "path": path, "api": api}, "clocks": clk, "verified": bad == 0}
+    # e2e: the reference's host-pointer wrapper (malloc + H2D + sort + D2H + free, gpu_radix_sort.h:510-541)
+    if path == "msb" and vb == 0 and not args.no_e2e:
+        lib.ref_msb_sort_keys_host.restype = ctypes.c_int
+        hk = torch.empty(n, dtype=kdt).pin_memory(); hk.copy_(src)
+        ho = torch.empty(n, dtype=kdt).pin_memory()
+        call = lambda: lib.ref_msb_sort_keys_host(ctypes.c_void_p(hk.data_ptr()), ctypes.c_ulonglong(n), ctypes.c_void_p(ho.data_ptr()), ctypes.c_int(kbits))
+        saved = os.dup(1); devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 1)
+        try:
+            call()
+            k = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            for _ in range(k):
+                call()
+            dt = (time.perf_counter() - t0) / k
+        finally:
+            os.dup2(saved, 1); os.close(devnull)
+        line["e2e"] = {"value": round(n / dt / 1e9, 3), "unit": "Gkeys/s", "h2d_bytes_per_step": n * kbits // 8, "d2h_bytes_per_step": n * kbits // 8,
+                       "ms_per_step": round(dt * 1e3, 3), "entry": "rdxsrt_unstable_sort_keys (host pointers)"}
+    else:
+        line["e2e"] = {"value": line["value"], "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS) + ["cfg5"])
+    ap.add_argument("--logn", type=int, default=0, help="override log2(keys per GPU)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        if torch.cuda.is_available():
+            torch.cuda.set_device(0)
+        wl = WORKLOADS["cfg3" if args.workload == "cfg5" else args.workload]
+        print(json.dumps(run_reference(args, wl)), flush=True)
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        line = run_ours_multi(args, rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+    else:
+        line = run_ours_single(args, WORKLOADS["cfg3" if args.workload == "cfg5" else args.workload])
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

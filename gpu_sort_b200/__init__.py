@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sort.so")
+LIB_PATH = os.environ.get("B200SORT_LIB") or os.path.join(_HERE, "libb200sort.so")   # env override: kernel-variant A/B runs (tools/)
 
 KEY_U32, KEY_U64, KEY_I32, KEY_I64, KEY_F32, KEY_F64 = range(6)
 KEY_BYTES = {KEY_U32: 4, KEY_U64: 8, KEY_I32: 4, KEY_I64: 8, KEY_F32: 4, KEY_F64: 8}
@@ -68,6 +68,10 @@ def _load():
     lib.b200_util_generate_keys.argtypes = [vp, u64, u64, u64, i32, u64, i32, u64, vp]
     lib.b200_util_iota.restype = i32
     lib.b200_util_iota.argtypes = [vp, u64, u64, i32, vp]
+    lib.b200_prof_enable.restype = i32
+    lib.b200_prof_enable.argtypes = [i32]
+    lib.b200_prof_report.restype = i32
+    lib.b200_prof_report.argtypes = [ctypes.c_char_p, sz]
     lib.b200_util_check.restype = i32
     lib.b200_util_check.argtypes = [vp, vp, u64, i32, i32, i32, vp, vp]
     return lib
@@ -285,3 +289,19 @@ def check(keys: torch.Tensor, values: Optional[torch.Tensor] = None, descending=
                                _ptr(out), _stream(stream)), "b200_util_check")
     r = out.cpu().numpy().view(np.uint64)
     return int(r[0]), int(r[1]), int(r[2]), int(r[3])
+
+
+def prof_enable(on: bool = True):
+    """Bracket every kernel launch of the library with CUDA events (b200_prof_enable)."""
+    _check(lib.b200_prof_enable(int(on)), "b200_prof_enable")
+
+
+def prof_report() -> dict:
+    """{kernel family: (launches, total ms)} since prof_enable / the last report (b200_prof_report); synchronises."""
+    buf = ctypes.create_string_buffer(8192)
+    _check(lib.b200_prof_report(buf, len(buf)), "b200_prof_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out

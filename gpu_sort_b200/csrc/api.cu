@@ -6,7 +6,38 @@
 #include "common.cuh"
 #include "sort_api.h"
 
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
 using namespace b200;
+
+// ---- per-kernel timing (sort_api.h: ProfScope) -----------------------------------------------------------------
+namespace b200 {
+int g_prof_enabled = 0;
+namespace {
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr; cudaEventCreate(&e); return e;
+}
+}  // namespace
+void prof_begin(const char* name, cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  ProfRec r{name, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, s);
+  g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, s);
+}
+}  // namespace b200
 
 namespace {
 
@@ -96,7 +127,40 @@ int sort_host(bool msb, const void* hk, const void* hv, uint64_t n, void* hko, v
 
 extern "C" {
 
-int b200_version(void) { return 100; }
+int b200_version(void) { return 101; }
+
+int b200_prof_enable(int enable) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+  g_prof_recs.clear();
+  g_prof_enabled = enable ? 1 : 0;
+  return 0;
+}
+
+int b200_prof_report(char* buf, size_t cap) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  std::vector<std::string> order;
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& r : g_prof_recs) {
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    if (e != cudaSuccess) return (int)e;
+    float ms = 0.f;
+    if ((e = cudaEventElapsedTime(&ms, r.e0, r.e1)) != cudaSuccess) return (int)e;
+    auto it = agg.find(r.name);
+    if (it == agg.end()) { order.push_back(r.name); agg[r.name] = {1, (double)ms}; }
+    else { it->second.first += 1; it->second.second += ms; }
+  }
+  std::string out;
+  char line[160];
+  for (auto& n : order) {
+    snprintf(line, sizeof line, "%s %d %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+    out += line;
+  }
+  if (buf && cap) { size_t m = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), m); buf[m] = 0; }
+  for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+  g_prof_recs.clear();
+  return 0;
+}
 
 const char* b200_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
 

@@ -8,6 +8,17 @@ namespace b200 {
 
 struct Twiddle;
 
+// Optional per-kernel timing (b200_prof_enable / b200_prof_report in the C ABI): when enabled, every launch site is
+// bracketed by two CUDA events on the launching stream.  Off by default -- a disabled scope costs one load and a branch.
+extern int g_prof_enabled;
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s; bool on;
+  ProfScope(const char* name, cudaStream_t stream) : s(stream), on(g_prof_enabled != 0) { if (on) prof_begin(name, s); }
+  ~ProfScope() { if (on) prof_end(s); }
+};
+
 template <typename K, int VB>
 cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, void* v0, void* v1, int* selector,
                           uint64_t n, const Twiddle& tw, int begin_bit, int end_bit, int allow_overwrite, cudaStream_t s);

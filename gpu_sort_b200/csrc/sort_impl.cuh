@@ -13,6 +13,7 @@
 #include "local_sort.cuh"
 #include "msb_sched.cuh"
 #include "partition.cuh"
+#include "sort_api.h"
 
 namespace b200 {
 
@@ -59,6 +60,7 @@ inline cudaError_t launch_partition(const PartArgs& a, uint32_t tiles_hint, cuda
   static int grid = 0;
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
+  ProfScope prof(a.splitters ? "range_partition" : (ORDERED ? "partition_lsb" : "partition_msb"), s);
   kernel<<<g, C::THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
@@ -72,6 +74,7 @@ inline cudaError_t launch_local(const LocalArgs& a, uint32_t items_hint, cudaStr
   static int grid = 0;
   if (!grid) B200_CHECK(persistent_grid(kernel, C::LOCAL_THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
+  ProfScope prof("local_sort", s);
   kernel<<<g, C::LOCAL_THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
@@ -163,8 +166,8 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     ha.keys = k0; ha.n = n; ha.num_passes = passes; ha.begin_bit = begin_bit; ha.end_bit = end_bit;
     ha.tw_in = 1; ha.tw = tw; ha.hist = hist;
     const int grid = (int)std::min<uint64_t>((uint64_t)num_sms() * 4, (n + 4095) / 4096);
-    hist_all_kernel<K><<<grid, HIST_THREADS, 0, s>>>(ha);
-    scan_bins_kernel<<<passes, RADIX, 0, s>>>(hist, 0);
+    { ProfScope prof("hist_all", s); hist_all_kernel<K><<<grid, HIST_THREADS, 0, s>>>(ha); }
+    { ProfScope prof("scan_bins", s); scan_bins_kernel<<<passes, RADIX, 0, s>>>(hist, 0); }
   }
 
   // ---- one partition launch per digit (per portion of < 2^30 keys)
@@ -257,9 +260,12 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
   }
 
   B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
-  msb_init_kernel<<<1, 32, 0, s>>>(segs0, ctr, n);
-  scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(segs0, &ctr->num_segs[0], tile_base, &ctr->num_tiles[0], max_tiles, &ctr->error, C::TILE);
-  fill_descs_kernel<<<sms * 2, 256, 0, s>>>(segs0, tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], descs, C::TILE);
+  {
+    ProfScope prof("msb_sched", s);
+    msb_init_kernel<<<1, 32, 0, s>>>(segs0, ctr, n);
+    scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(segs0, &ctr->num_segs[0], tile_base, &ctr->num_tiles[0], max_tiles, &ctr->error, C::TILE);
+    fill_descs_kernel<<<sms * 2, 256, 0, s>>>(segs0, tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], descs, C::TILE);
+  }
 
   for (int L = 0; L < LEVELS; ++L) {
     const int shift = KEY_BITS - 8 * (L + 1);
@@ -268,11 +274,11 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
     const void* in_k = kbuf[L & 1]; void* out_k = kbuf[(L + 1) & 1];
     const void* in_v = vbuf[L & 1]; void* out_v = vbuf[(L + 1) & 1];
 
-    level_prep_kernel<<<sms * 2, 512, 0, s>>>(seg_hist, &ctr->num_segs[L], status, &ctr->num_tiles[L]);
+    { ProfScope prof("msb_sched", s); level_prep_kernel<<<sms * 2, 512, 0, s>>>(seg_hist, &ctr->num_segs[L], status, &ctr->num_tiles[L]); }
     SegHistArgs ha{};
     ha.keys = in_k; ha.segs = cur; ha.descs = descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
     ha.seg_hist = seg_hist; ha.tile = C::TILE; ha.shift = shift; ha.tw_in = (L == 0); ha.tw = tw;
-    seg_hist_kernel<K><<<sms * 4, HIST_THREADS, 0, s>>>(ha);
+    { ProfScope prof("seg_hist", s); seg_hist_kernel<K><<<sms * 4, HIST_THREADS, 0, s>>>(ha); }
 
     ClassifyArgs ca{};
     ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = seg_hist; ca.bins = bins;
@@ -281,7 +287,7 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
     ca.error = &ctr->error; ca.shift = shift; ca.local_cap = C::LOCAL_CAP; ca.merge_cap = C::MERGE_CAP;
     ca.out_buf = (uint32_t)((L + 1) & 1);
     const int cgrid = (int)std::min<uint32_t>((max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
-    classify_kernel<<<L == 0 ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca);
+    { ProfScope prof("msb_sched", s); classify_kernel<<<L == 0 ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca); }
 
     PartArgs pa{};
     pa.keys_in = in_k; pa.keys_out = out_k; pa.vals_in = in_v; pa.vals_out = out_v;
@@ -291,6 +297,7 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
     B200_CHECK((launch_partition<K, VB, false>(pa, max_tiles, s)));
 
     if (L + 1 < LEVELS) {
+      ProfScope prof("msb_sched", s);
       scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(nxt, &ctr->num_segs[L + 1], tile_base, &ctr->num_tiles[L + 1], max_tiles, &ctr->error, C::TILE);
       fill_descs_kernel<<<sms * 2, 256, 0, s>>>(nxt, tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], descs, C::TILE);
     }

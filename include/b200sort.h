@@ -140,6 +140,16 @@ B200_API int b200_util_iota(void* d_values, uint64_t num_items, uint64_t start, 
 B200_API int b200_util_check(const void* d_keys, const void* d_values, uint64_t num_items, int key_type, int value_bytes,
                     int descending, uint64_t* d_out, b200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Per-kernel timing for the benchmark's roofline figure (replaces the reference's BM_START/STOP_CUDA_EVENT macros
+ * around histogram / pfx_sum / scatter / local_sort, msb/src/sort/gpu_radix_sort.h:266-269,278,284 and
+ * msb/external/benchmark/benchmark.h:640-733).  While enabled, every kernel launch of the library is bracketed by CUDA
+ * events on the launching stream.  b200_prof_report synchronises on them and writes one text line per kernel family,
+ * "<name> <launches> <total ms>", then clears the records.  Off by default.
+ * ------------------------------------------------------------------------------------------------------------------ */
+B200_API int b200_prof_enable(int enable);
+B200_API int b200_prof_report(char* buf, size_t buf_bytes);
+
 #ifdef __cplusplus
 }
 #endif
