@@ -77,52 +77,110 @@ static __global__ void __launch_bounds__(RADIX) scan_bins_kernel(unsigned long l
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// MSB: per-segment histograms over the level's tile list.
+// MSD levels: digit histogram of every TILE of the level (replaces rdxsrt_histogram + its per-block histograms,
+// msb/src/sort/cuda_radix_sort.h:657-802, and the decoupled look-back of a onesweep pass: with the counts of every tile
+// known before the scatter starts, a tile's destination is a pure function of three prefetchable loads).
+//   tile_off[t][d]  = number of keys with digit d in the tiles of t's segment that precede t INSIDE t's group
+//   group_tail[g][d]= the same running count at the end of group g (over the last segment the group touches)
+//   group_flag[g]   = 1 if a segment starts inside group g
+//   seg_hist[s][d]  = keys with digit d in segment s                                  (global atomics, zeroed)
+// A group = HIST_GROUP consecutive entries of the tile list (segments are contiguous in the list); one CTA handles a
+// whole group, so the running counts live in registers.  group_carry_kernel then chains the groups.
 // ---------------------------------------------------------------------------------------------------------
-struct SegHistArgs {
+constexpr int HIST_GROUP = 16;
+
+struct TileHistArgs {
   const void* keys;
-  const Seg* segs; const TileDesc* descs; const uint32_t* num_tiles_ptr;
-  uint32_t* seg_hist;                   // [segment][256], zeroed
-  int tile;                             // keys per tile (same tiling as the partition kernel)
-  int shift; int tw_in; Twiddle tw;
+  const TileDesc* descs; const uint32_t* num_tiles_ptr;
+  uint32_t* tile_off; uint32_t* group_tail; uint32_t* group_flag;
+  uint32_t* seg_hist;
+  int shift; uint32_t mask; int tw_in; Twiddle tw;
 };
 
 template <typename K>
-__global__ void __launch_bounds__(HIST_THREADS) seg_hist_kernel(const __grid_constant__ SegHistArgs a) {
+__global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_constant__ TileHistArgs a) {
   __shared__ uint32_t sh[RADIX];
   const K* __restrict__ keys = reinterpret_cast<const K*>(a.keys);
   const uint32_t num_tiles = *a.num_tiles_ptr;
-  const uint32_t per = (num_tiles + gridDim.x - 1) / gridDim.x;
-  const uint32_t t0 = per * blockIdx.x, t1 = min(t0 + per, num_tiles);
-  if (t0 >= t1) return;
-  if (threadIdx.x < RADIX) sh[threadIdx.x] = 0;
-  __syncthreads();
-  uint32_t cur_seg = a.descs[t0].seg;
-  for (uint32_t t = t0; t < t1; ++t) {
-    const TileDesc td = a.descs[t];
-    if (td.seg != cur_seg) {            // block-uniform: flush the finished segment
+  const uint32_t num_groups = (num_tiles + HIST_GROUP - 1) / HIST_GROUP;
+  const unsigned tid = threadIdx.x;
+  const int shift = a.shift; const uint32_t mask = a.mask;
+  const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+  using S = typename std::make_signed<K>::type;
+  auto count = [&](K k) {
+    if (a.tw_in) k = (K)(k ^ (((K)((S)k >> (sizeof(K) * 8 - 1)) & fl) | sg) ^ fp);
+    atomicAdd(&sh[digit_of<K>(k, shift, mask)], 1u);
+  };
+  for (uint32_t g = blockIdx.x; g < num_groups; g += gridDim.x) {
+    const uint32_t t0 = g * HIST_GROUP, t1 = min(t0 + HIST_GROUP, num_tiles);
+    uint32_t run = 0, acc = 0, flag = 0, cur_seg = a.descs[t0].seg;      // digit owners (tid < 256)
+    for (uint32_t t = t0; t < t1; ++t) {
+      const TileDesc td = a.descs[t];
+      if (tid < RADIX) sh[tid] = 0;
       __syncthreads();
-      if (threadIdx.x < RADIX) {
-        const uint32_t c = sh[threadIdx.x];
-        if (c) atomicAdd(&a.seg_hist[(uint64_t)cur_seg * RADIX + threadIdx.x], c);
-        sh[threadIdx.x] = 0;
+      const uint32_t cnt = td.cnt;
+      const K* p = keys + td.off;
+      // 16-byte vector loads over the aligned body of the tile, scalar head and tail
+      constexpr uint32_t VEC = 16 / sizeof(K);
+      const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(p) & 15u) / sizeof(K));
+      const uint32_t head = min(cnt, mis ? VEC - mis : 0u);
+      const uint32_t nvec = (cnt - head) / VEC;
+      const uint4* pv = reinterpret_cast<const uint4*>(p + head);
+      for (uint32_t i = tid; i < nvec; i += HIST_THREADS) {
+        const uint4 q = pv[i];
+        if (sizeof(K) == 4) { count((K)q.x); count((K)q.y); count((K)q.z); count((K)q.w); }
+        else { count((K)(((uint64_t)q.y << 32) | q.x)); count((K)(((uint64_t)q.w << 32) | q.z)); }
       }
+      if (tid < head) count(p[tid]);
+      const uint32_t tail0 = head + nvec * VEC;
+      if (tail0 + tid < cnt) count(p[tail0 + tid]);
       __syncthreads();
-      cur_seg = td.seg;
+      if (tid < RADIX) {
+        const uint32_t c = sh[tid];
+        if (td.tile_in_seg == 0) {                       // a segment starts here: close the previous one
+          if (acc) atomicAdd(&a.seg_hist[(uint64_t)cur_seg * RADIX + tid], acc);
+          acc = 0; run = 0; flag = 1; cur_seg = td.seg;
+        }
+        a.tile_off[(uint64_t)t * RADIX + tid] = run;
+        run += c; acc += c;
+      }
     }
-    const uint32_t cnt = td.cnt;
-    const K* p = keys + td.off;
-    for (uint32_t i = threadIdx.x; i < cnt; i += HIST_THREADS) {
-      K k = p[i];
-      if (a.tw_in) k = twiddle_in<K>(k, a.tw);
-      const uint32_t d = digit_of<K>(k, a.shift, 0xFFu);
-      atomicAdd(&sh[d], 1u);
+    if (tid < RADIX) {
+      if (acc) atomicAdd(&a.seg_hist[(uint64_t)cur_seg * RADIX + tid], acc);
+      a.group_tail[(uint64_t)g * RADIX + tid] = run;
+      if (tid == 0) a.group_flag[g] = flag;
     }
   }
+}
+
+// carry[g][d] = keys with digit d in the tiles of the segment that CONTINUES into group g from earlier groups, i.e. a
+// segmented exclusive scan of group_tail along the group axis (state after group g: flag[g] ? tail[g] : state + tail[g]).
+// Grid = 8 CTAs (one per slab of 32 digits, lane = digit, 128-byte rows); the 32 warps of a CTA split the group range.
+constexpr int CARRY_WARPS = 32;
+static __global__ void __launch_bounds__(CARRY_WARPS * 32) group_carry_kernel(const uint32_t* group_tail, const uint32_t* group_flag, uint32_t* carry,
+                                                                              const uint32_t* num_tiles_ptr) {
+  __shared__ uint32_t p_sum[CARRY_WARPS][32];
+  __shared__ uint32_t p_flag[CARRY_WARPS];
+  const uint32_t num_groups = (*num_tiles_ptr + HIST_GROUP - 1) / HIST_GROUP;
+  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const unsigned d = blockIdx.x * 32 + lane;
+  const uint32_t per = (num_groups + CARRY_WARPS - 1) / CARRY_WARPS;
+  const uint32_t g0 = min(per * w, num_groups), g1 = min(g0 + per, num_groups);
+  uint32_t sum = 0, flag = 0;
+  for (uint32_t g = g0; g < g1; ++g) {
+    const uint32_t t = group_tail[(uint64_t)g * RADIX + d];
+    const uint32_t f = group_flag[g];
+    sum = f ? t : sum + t; flag |= f;
+  }
+  p_sum[w][lane] = sum;
+  if (lane == 0) p_flag[w] = flag;
   __syncthreads();
-  if (threadIdx.x < RADIX) {
-    const uint32_t c = sh[threadIdx.x];
-    if (c) atomicAdd(&a.seg_hist[(uint64_t)cur_seg * RADIX + threadIdx.x], c);
+  uint32_t state = 0;
+  for (unsigned ww = 0; ww < w; ++ww) state = p_flag[ww] ? p_sum[ww][lane] : state + p_sum[ww][lane];
+  for (uint32_t g = g0; g < g1; ++g) {
+    carry[(uint64_t)g * RADIX + d] = state;
+    const uint32_t t = group_tail[(uint64_t)g * RADIX + d];
+    state = group_flag[g] ? t : state + t;
   }
 }
 

@@ -23,7 +23,7 @@
 namespace b200 {
 
 struct LocalArgs {
-  void* keys[2]; void* vals[2];          // the two ping-pong buffers
+  void* keys[3]; void* vals[3];          // the ping-pong buffers (LocalItem::src indexes them)
   void* keys_final; void* vals_final;
   const LocalItem* items; const uint32_t* num_items_ptr;
   int tw_in;                             // keys still in caller form (single-tile sorts)

@@ -37,7 +37,9 @@ struct ClassifyArgs {
   Seg* next_segs; uint32_t* num_next_ptr; uint32_t max_segs;
   LocalItem* locals; uint32_t* num_locals_ptr; uint32_t max_locals;
   uint32_t* error;
-  int shift;                    // bit position of this level's digit; `shift` low bits remain below it
+  int shift;                    // bit position of this level's digit; bits [begin_bit, shift) remain below it
+  int nb;                       // width of this level's digit (8, or less on the last level of a bit sub-range)
+  int last;                     // no bits remain below this digit: every sub-bucket is final after the scatter
   uint32_t local_cap, merge_cap;
   uint32_t out_buf;             // ping-pong buffer the level scatters into
 };
@@ -72,7 +74,7 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
       run += c[i];
     }
     __syncwarp();
-    if (a.shift == 0) continue;       // last digit: every sub-bucket is final after the scatter
+    if (a.last) continue;             // last digit: every sub-bucket is final after the scatter
     // classify + merge, serial over the 256 digits (lane 0), staged in shared memory
     uint32_t nloc = 0, nseg = 0;
     if (lane == 0) {
@@ -80,7 +82,7 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
       auto flush = [&]() {
         if (pend_n) {
           LocalItem it; it.off = pend_off; it.cnt = pend_sum;
-          it.nbits = (uint16_t)(pend_n > 1 ? a.shift + 8 : a.shift); it.src = (uint16_t)a.out_buf;
+          it.nbits = (uint16_t)(pend_n > 1 ? a.shift + a.nb : a.shift); it.src = (uint16_t)a.out_buf;
           s_loc[w][nloc++] = it;
           pend_n = 0; pend_sum = 0;
         }

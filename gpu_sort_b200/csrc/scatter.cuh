@@ -1,0 +1,457 @@
+// scatter.cuh -- the bucket scatter: one read + one write sweep that splits every segment by one digit.
+//
+// One kernel template serves
+//   MODE_SEG   : every level of the MSB hybrid sort (many segments; tiles come from a device-built TileDesc list; a
+//                tile reserves its output chunk per digit with one global atomicAdd, so tiles are independent and the
+//                order inside a sub-bucket is arbitrary -- exactly the freedom the reference takes,
+//                msb/src/sort/cuda_radix_sort.h:408-417).  Replaces rdxsrt_partition_keys (cuda_radix_sort.h:363-479).
+//   MODE_LSB   : every pass of the stable LSB sort (one segment, onesweep style: digit starts from the up-front
+//                histogram, tile prefix by decoupled look-back, stable in-tile ranking).  Replaces
+//                DeviceRadixSortDownsweepKernel (lsb/cub/cub/device/dispatch/dispatch_radix_sort.cuh:164-196).
+//   MODE_RANGE : the multi-GPU send partition (stable; digit = destination rank by key range).
+//
+// The kernel is bound by instruction issue and shared-memory traffic long before HBM (DESIGN.md "Kernels"), so the
+// per-key path is kept minimal: full tiles take a path without any bounds checks, the order-preserving transform
+// is applied in its own uniform-branch loop only on the first / last sweep, destinations are per-digit 64-bit
+// pointers in shared memory (one LDS.64 + one IMAD.WIDE per key), and the digit is a 2-instruction shift+mask.
+//
+// Structure (persistent CTAs):
+//   * the NEXT tile's keys (and values) are staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier)
+//     issued by one producer thread while the current tile is being ranked;
+//   * keys are ranked from registers: MSB -> one shared-memory atomicAdd-with-return per key; LSB -> lanes holding the
+//     same digit find each other through an atomicOr of their lane bit into a per-warp match mask and rank against
+//     warp-private running counters (tools/ubench_rank.cu measured the candidates on B200);
+//   * digit owners (threads 0..255) reserve / look back and publish one destination pointer per digit;
+//   * keys (and values) are reordered through the consumed staging buffer so every digit's run leaves as consecutive
+//     addresses (coalesced stores; adjacent tiles complete each other's partial sectors in the 126 MB L2).
+#pragma once
+#include "async.cuh"
+#include "common.cuh"
+#include "hist.cuh"
+
+namespace b200 {
+
+enum { MODE_SEG = 0, MODE_LSB = 1, MODE_RANGE = 2 };
+
+struct ScatterArgs {
+  const void* keys_in; void* keys_out;
+  const void* vals_in; void* vals_out;
+  const TileDesc* descs;          // MODE_SEG: tile -> (offset, count, segment, tile in segment)
+  const uint32_t* num_tiles_ptr;  // MODE_SEG: device-side tile count
+  uint32_t num_tiles;             // MODE_LSB / MODE_RANGE
+  uint64_t base, n;               // MODE_LSB / MODE_RANGE: the launch covers keys [base, base+n)
+  const uint64_t* bins;           // MODE_SEG: [segment][256] absolute output index of the start of each sub-bucket;
+                                  // otherwise [256] absolute output index of the start of each digit
+  const uint32_t* tile_off;       // MODE_SEG: [tile][256]  keys of the same (segment, digit) in earlier tiles of the tile's group
+  const uint32_t* carry;          // MODE_SEG: [group][256] ... and in earlier groups (tile_hist_kernel / group_carry_kernel)
+  uint64_t* bins_next;            // MODE_LSB / MODE_RANGE: the last tile writes bins + portion counts here (or nullptr)
+  uint32_t* status;               // MODE_LSB / MODE_RANGE: [tile][256] look-back words, zeroed before the launch
+  uint32_t* ticket;               // MODE_LSB / MODE_RANGE: zeroed before the launch
+  int shift; uint32_t mask;
+  int tw_in, tw_out;
+  Twiddle tw;
+  const uint32_t* splitters; int num_parts;     // MODE_RANGE: digit = #{ j < num_parts-1 : splitters[j] <= (key >> shift) }
+};
+
+constexpr int MAX_PARTS = 16;
+
+struct TileGeom {     // per staging slot, written by the producer thread
+  uint64_t off;       // first key index
+  uint32_t cnt, seg, tile_in_seg, tile, skew, vskew;
+};
+
+template <typename K, int VB, int THREADS, int IPT, int MODE, bool ORD>
+struct ScatterSmem {
+  static constexpr int TILE = THREADS * IPT;
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr bool ORDERED = MODE != MODE_SEG || ORD;
+  using V = typename ValType<VB>::type;
+  static constexpr int SLACK = 16 / sizeof(K), VSLACK = 16 / sizeof(V);
+  alignas(16) K stage[2][TILE + SLACK];
+  alignas(16) V vstage[VB ? 2 : 1][VB ? TILE + VSLACK : 1];
+  K* kptr[RADIX];                                   // per digit: keys_out + (global start - start inside the tile)
+  V* vptr[VB ? RADIX : 1];
+  alignas(16) uint32_t match[ORDERED ? 2 : 1][ORDERED ? WARPS * RADIX : 1];   // per-warp match masks, two alternating sets
+  alignas(16) uint16_t wcnt[ORDERED ? WARPS * RADIX : 2];                     // per-warp counters, later per-warp start positions
+  uint32_t cnt[RADIX];                              // MSB: tile histogram (atomic ranking counters)
+  uint32_t bin_start[RADIX];                        // tile-local exclusive start of each digit
+  uint32_t scratch[8];
+  alignas(8) uint64_t bar[2];
+  TileGeom geom[2];
+  uint32_t split[MAX_PARTS];
+  uint32_t skewed;                                  // MSB: the previous tile had a dominant digit -> aggregate per warp
+};
+
+template <typename K, int MODE>
+__device__ __forceinline__ uint32_t scatter_digit(K k, int shift, uint32_t mask, const uint32_t* split, int num_parts) {
+  if (MODE != MODE_RANGE) return digit_of<K>(k, shift, mask);
+  const uint32_t b = (uint32_t)(k >> shift);
+  uint32_t d = 0;
+#pragma unroll
+  for (int j = 0; j < MAX_PARTS - 1; ++j) d += (j < num_parts - 1 && b >= split[j]) ? 1u : 0u;
+  return d;
+}
+
+// 32-bit / 64-bit forms of the order-preserving transform with the masks already narrowed to K (3 instructions).
+template <typename K>
+__device__ __forceinline__ K tw_apply_in(K k, K sign, K fl, K flip) {
+  using S = typename std::make_signed<K>::type;
+  return (K)(k ^ (((K)((S)k >> (sizeof(K) * 8 - 1)) & fl) | sign) ^ flip);
+}
+template <typename K>
+__device__ __forceinline__ K tw_apply_out(K k, K sign, K fl, K flip) {
+  using S = typename std::make_signed<K>::type;
+  k = (K)(k ^ flip);
+  return (K)(k ^ (((K)(~(K)((S)k >> (sizeof(K) * 8 - 1))) & fl) | sign));
+}
+
+// Store through a per-digit destination pointer kept in shared memory (known to be global memory: plain STG, no
+// generic-address resolution).
+template <typename T>
+__device__ __forceinline__ void st_global(T* base, uint32_t idx, T v) {
+  T* p = base + idx;
+  if (sizeof(T) == 4) asm volatile("st.global.b32 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
+  else asm volatile("st.global.b64 [%0], %1;" ::"l"(p), "l"((uint64_t)v) : "memory");
+}
+
+#ifndef LB_BATCH
+#define LB_BATCH 8
+#endif
+#ifndef LB_POS
+#define LB_POS 0
+#endif
+// Decoupled look-back for one digit (called by the digit's owner thread): sums the aggregates of the predecessor tiles
+// down to the nearest one that already knows its inclusive prefix, LB_BATCH predecessors per round trip (the loads of
+// a batch are independent, so a walk of depth D costs ~D/LB_BATCH L2 latencies).  A stale word is still valid (an
+// aggregate is only ever upgraded to a prefix), so only not-yet-published words are re-read.  Publishes this tile's
+// inclusive prefix and returns its exclusive prefix.
+__device__ __forceinline__ uint32_t lookback(const uint32_t* sbase, uint32_t tile, uint32_t tile_in_seg, uint32_t* stw, uint32_t my_total) {
+  uint32_t excl_g = 0;
+  int64_t t = (int64_t)tile - 1;
+  const int64_t t_first = (int64_t)tile - (int64_t)tile_in_seg;
+  bool done = false;
+  while (!done) {
+    uint32_t s[LB_BATCH];
+#pragma unroll
+    for (int j = 0; j < LB_BATCH; ++j) s[j] = (t - j >= t_first) ? ld_status(sbase + (uint64_t)(t - j) * RADIX) : ST_PREFIX;
+#pragma unroll
+    for (int j = 0; j < LB_BATCH; ++j) {
+      if (!done) {
+        uint32_t v = s[j];
+        while ((v >> 30) == 0) { __nanosleep(20); v = ld_status(sbase + (uint64_t)(t - j) * RADIX); }
+        excl_g += v & ST_VALUE_MASK;
+        done = (v & ST_PREFIX) != 0;
+      }
+    }
+    t -= LB_BATCH;
+  }
+  st_status(stw, ST_PREFIX | (excl_g + my_total));
+  return excl_g;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One tile.  FULL = the tile holds exactly TILE keys (no bounds checks anywhere).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename K, int VB, int THREADS, int IPT, int MODE, bool ORD, bool FULL>
+__device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K, VB, THREADS, IPT, MODE, ORD>& sm, const TileGeom& g, int slot,
+                                             uint32_t num_tiles, uint32_t it) {
+  using SM = ScatterSmem<K, VB, THREADS, IPT, MODE, ORD>;
+  using V = typename SM::V;
+  constexpr int TILE = SM::TILE, WARPS = SM::WARPS;
+  constexpr bool ORDERED = SM::ORDERED;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const uint32_t cnt = FULL ? (uint32_t)TILE : g.cnt;
+  const int shift = a.shift; const uint32_t mask = a.mask;
+  K* __restrict__ st = &sm.stage[slot][0];
+  V* __restrict__ vst = &sm.vstage[VB ? slot : 0][0];
+
+  // ---- keys of this tile: shared memory (TMA-staged) -> registers
+  mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
+  K key[IPT];
+  const uint32_t ibase = ORDERED ? w * (32u * IPT) + lane : tid;     // index of item j: ibase + j * istep
+  constexpr uint32_t istep = ORDERED ? 32u : (uint32_t)THREADS;
+  {
+    const K* __restrict__ src = st + g.skew + ibase;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      if (FULL) key[j] = src[j * istep];
+      else key[j] = (ibase + j * istep < cnt) ? src[j * istep] : (K)~(K)0;
+    }
+  }
+  if (a.tw_in) {
+    const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      if (FULL) key[j] = tw_apply_in<K>(key[j], sg, fl, fp);
+      else key[j] = (ibase + j * istep < cnt) ? tw_apply_in<K>(key[j], sg, fl, fp) : (K)~(K)0;
+    }
+  }
+
+  // ---- rank inside the tile
+  uint32_t pos[IPT];
+  uint32_t my_total = 0;
+  if (!ORDERED) {
+    if (tid < RADIX) sm.cnt[tid] = 0;
+    __syncthreads();
+    if (!sm.skewed) {
+#pragma unroll
+      for (int j = 0; j < IPT; ++j)
+        if (FULL || ibase + j * istep < cnt) pos[j] = atomicAdd(&sm.cnt[digit_of<K>(key[j], shift, mask)], 1u);
+    } else {
+      // dominant digit: same-address shared-memory atomics with return serialise (~11x slower on constant input,
+      // profiles/ubench_rank_r01.jsonl) -> a warp whose 32 digits agree adds once for everybody
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        const bool v = FULL || ibase + j * istep < cnt;
+        const unsigned d = digit_of<K>(key[j], shift, mask);
+        const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
+        if (__all_sync(0xffffffffu, v && d == d0)) {
+          unsigned b = 0;
+          if (lane == 0) b = atomicAdd(&sm.cnt[d0], 32u);
+          pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane;
+        } else if (v) {
+          pos[j] = atomicAdd(&sm.cnt[d], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < RADIX) my_total = sm.cnt[tid];
+  } else {
+    // stable ranking.  Row j of a warp = its 32 keys j*32 .. j*32+31 of the warp's contiguous share; rows are ranked in
+    // order, lanes in order inside a row.  Lanes with equal digits meet in match[j&1][w][d] (atomicOr of the lane bit);
+    // the lowest such lane adds the row's count to the warp's running counter and hands the old value to its peers.
+    uint4* z = reinterpret_cast<uint4*>(sm.match);
+    for (int i = tid; i < 2 * WARPS * RADIX / 4; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    uint4* zc = reinterpret_cast<uint4*>(sm.wcnt);
+    for (int i = tid; i < WARPS * RADIX / 8; i += THREADS) zc[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    uint16_t* wc = sm.wcnt + w * RADIX;
+    const unsigned lt = (1u << lane) - 1u, lbit = 1u << lane;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      uint32_t* wm = sm.match[j & 1] + w * RADIX;
+      const unsigned d = scatter_digit<K, MODE>(key[j], shift, mask, sm.split, a.num_parts);   // padding keys (all ones) rank last
+      atomicOr(&wm[d], lbit);
+      __syncwarp();
+      const unsigned peers = wm[d];
+      __syncwarp();
+      const unsigned below = __popc(peers & lt);
+      unsigned b = 0;
+      if (below == 0) { b = wc[d]; wc[d] = (uint16_t)(b + __popc(peers)); wm[d] = 0; }
+      b = __shfl_sync(0xffffffffu, b, __ffs(peers) - 1);
+      pos[j] = b + below;
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+#pragma unroll
+      for (int ww = 0; ww < WARPS; ++ww) my_total += sm.wcnt[ww * RADIX + tid];
+      if (!FULL && tid == scatter_digit<K, MODE>((K)~(K)0, shift, mask, sm.split, a.num_parts)) my_total -= (uint32_t)TILE - cnt;   // padding
+    }
+  }
+
+  // ---- digit owners: reserve (MSB) / publish the aggregate (LSB) as early as possible, then the tile-local scan
+  uint64_t gstart = 0;
+  uint32_t excl_g = 0;
+  uint32_t* stw = nullptr;
+  const bool first = g.tile_in_seg == 0;
+  if (tid < RADIX) {
+    if (MODE == MODE_SEG) {
+      // destination = start of the (segment, digit) sub-bucket + keys of it in earlier tiles: three independent loads whose
+      // latency hides behind the scan and the shared-memory reorder below
+      const uint32_t grp = g.tile / HIST_GROUP;
+      const bool continues = g.tile - g.tile_in_seg < grp * HIST_GROUP;       // the segment started in an earlier group
+      gstart = a.bins[(uint64_t)g.seg * RADIX + tid] + a.tile_off[(uint64_t)g.tile * RADIX + tid];
+      if (continues) gstart += a.carry[(uint64_t)grp * RADIX + tid];
+    } else {
+      stw = a.status + (uint64_t)g.tile * RADIX + tid;
+      st_status(stw, (first ? ST_PREFIX : ST_AGG) | my_total);
+      if (LB_POS == 1 && !first) excl_g = lookback(a.status + tid, g.tile, g.tile_in_seg, stw, my_total);
+    }
+  }
+  uint32_t inc = my_total;
+  if (tid < RADIX) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) sm.scratch[w] = inc;
+  }
+  __syncthreads();
+  uint32_t my_excl = 0;
+  if (tid < RADIX) {
+    uint32_t woff = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) woff += ((unsigned)j < w) ? sm.scratch[j] : 0u;
+    my_excl = woff + inc - my_total;
+    if (!ORDERED) {
+      sm.bin_start[tid] = my_excl;
+    } else {
+      uint32_t run = my_excl;
+#pragma unroll
+      for (int ww = 0; ww < WARPS; ++ww) {
+        const uint32_t c = sm.wcnt[ww * RADIX + tid];
+        sm.wcnt[ww * RADIX + tid] = (uint16_t)run;
+        run += c;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- reorder through shared memory (every thread has its keys in registers: the staging buffer is reused)
+  if (!ORDERED) {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j)
+      if (FULL || ibase + j * istep < cnt) { pos[j] += sm.bin_start[digit_of<K>(key[j], shift, mask)]; st[pos[j]] = key[j]; }
+  } else {
+    const uint16_t* wc = sm.wcnt + w * RADIX;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      pos[j] += wc[scatter_digit<K, MODE>(key[j], shift, mask, sm.split, a.num_parts)];
+      if (FULL || pos[j] < cnt) st[pos[j]] = key[j];        // padding keys rank after every real key: pos >= cnt
+    }
+  }
+  V val[VB ? IPT : 1];
+  if (VB) {
+    const V* __restrict__ vsrc = vst + g.vskew + ibase;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j)
+      if (FULL || ibase + j * istep < cnt) val[j] = vsrc[j * istep];
+  }
+
+  // ---- digit owners: global start of this tile's run of every digit -> destination pointers
+  if (tid < RADIX) {
+    if (MODE != MODE_SEG) {
+      if (LB_POS == 0) excl_g = first ? 0u : lookback(a.status + tid, g.tile, g.tile_in_seg, stw, my_total);
+      gstart = a.bins[tid] + excl_g;
+      if (a.bins_next != nullptr && g.tile == num_tiles - 1) a.bins_next[tid] = gstart + my_total;
+    }
+    sm.kptr[tid] = reinterpret_cast<K*>(a.keys_out) + (gstart - my_excl);
+    if (VB) sm.vptr[tid] = reinterpret_cast<V*>(a.vals_out) + (gstart - my_excl);
+  }
+  __syncthreads();        // keys are in place, every thread has read its values, kptr/vptr are published
+  if (VB) {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j)
+      if (FULL || (ORDERED ? pos[j] < cnt : ibase + j * istep < cnt)) vst[pos[j]] = val[j];
+    __syncthreads();
+  }
+
+  // ---- coalesced write-out: consecutive positions of one digit are consecutive output addresses
+  if (a.tw_out) {
+    const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      const uint32_t p = j * THREADS + tid;
+      if (FULL || p < cnt) {
+        const K k = st[p];
+        const uint32_t d = scatter_digit<K, MODE>(k, shift, mask, sm.split, a.num_parts);
+        st_global<K>(sm.kptr[d], p, tw_apply_out<K>(k, sg, fl, fp));
+        if (VB) st_global<V>(sm.vptr[d], p, vst[p]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      const uint32_t p = j * THREADS + tid;
+      if (FULL || p < cnt) {
+        const K k = st[p];
+        const uint32_t d = scatter_digit<K, MODE>(k, shift, mask, sm.split, a.num_parts);
+        st_global<K>(sm.kptr[d], p, k);
+        if (VB) st_global<V>(sm.vptr[d], p, vst[p]);
+      }
+    }
+  }
+  if (!ORDERED) {
+    // the next tile aggregates per warp if this one had a dominant digit (tiles of a CTA are neighbours in key space)
+    const int sk = __syncthreads_or(my_total > (uint32_t)TILE / 4);
+    if (tid == 0) sm.skewed = sk ? 1u : 0u;
+  } else {
+    __syncthreads();
+  }
+}
+
+template <typename K, int VB, int THREADS, int IPT, int MODE, bool ORD>
+__global__ void __launch_bounds__(THREADS, 2) scatter_kernel(const __grid_constant__ ScatterArgs a) {
+  using SM = ScatterSmem<K, VB, THREADS, IPT, MODE, ORD>;
+  using V = typename SM::V;
+  constexpr int TILE = SM::TILE;
+  constexpr bool ORDERED = SM::ORDERED;
+  constexpr unsigned PRODUCER = THREADS - 1;     // not a digit owner (THREADS > 256)
+  static_assert(THREADS > RADIX, "producer thread must not own a digit");
+  static_assert(TILE < 65536, "per-warp start positions are 16-bit");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  const unsigned tid = threadIdx.x;
+  const K* __restrict__ keys_in = reinterpret_cast<const K*>(a.keys_in);
+  const V* __restrict__ vals_in = reinterpret_cast<const V*>(a.vals_in);
+  const uint32_t num_tiles = MODE == MODE_SEG ? *a.num_tiles_ptr : a.num_tiles;
+
+  // producer: describe tile `t`, arm the slot's barrier and launch the bulk copies of its keys (and values)
+  auto stage_tile = [&](int slot, uint32_t t, const TileDesc& td) {
+    TileGeom g;
+    g.tile = t; g.skew = 0; g.vskew = 0;
+    if (t < num_tiles) {
+      if (MODE == MODE_SEG) { g.off = td.off; g.cnt = td.cnt; g.seg = td.seg; g.tile_in_seg = td.tile_in_seg; }
+      else {
+        const uint64_t rel = (uint64_t)t * TILE;
+        g.off = a.base + rel; g.cnt = (uint32_t)(a.n - rel < (uint64_t)TILE ? a.n - rel : (uint64_t)TILE);
+        g.seg = 0; g.tile_in_seg = t;
+      }
+      const BulkWindow<K> bw(keys_in, g.off, g.cnt);
+      g.skew = bw.skew;
+      uint32_t bytes = bw.bytes;
+      fence_proxy_async();
+      if (VB) {
+        const BulkWindow<V> vw(vals_in, g.off, g.cnt);
+        g.vskew = vw.skew;
+        bytes += vw.bytes;
+        mbar_expect_tx(&sm.bar[slot], bytes);
+        bulk_g2s(&sm.vstage[VB ? slot : 0][0], vw.src, vw.bytes, &sm.bar[slot]);
+      } else {
+        mbar_expect_tx(&sm.bar[slot], bytes);
+      }
+      bulk_g2s(&sm.stage[slot][0], bw.src, bw.bytes, &sm.bar[slot]);
+    } else {
+      g.off = 0; g.cnt = 0; g.seg = 0; g.tile_in_seg = 0;
+    }
+    sm.geom[slot] = g;
+  };
+
+  // Tile sequence.  Ordered modes: dynamic tickets; MSB: tiles are independent and dealt round-robin.  The producer
+  // knows its next tile one full iteration ahead (ticket / descriptor fetched during the previous tile), so the TMA
+  // prefetch into the free slot goes out at the very top of an iteration.  Holding tickets ahead cannot deadlock the
+  // look-back: a CTA processes its tiles in increasing order, hence the lowest unfinished tile of the launch is always
+  // the one its CTA is working on, it only waits for lower (finished) tiles, and all CTAs are co-resident.
+  uint32_t tk_a = 0, tk_b = 0;      // producer only: tile of the next / the following iteration
+  TileDesc td_a{}, td_b{};
+  if (tid == PRODUCER) {
+    mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1);
+    mbar_fence_init();
+    const uint32_t t0 = MODE != MODE_SEG ? atomicAdd(a.ticket, 1u) : blockIdx.x;
+    tk_a = MODE != MODE_SEG ? atomicAdd(a.ticket, 1u) : t0 + gridDim.x;
+    TileDesc td{};
+    if (MODE == MODE_SEG && t0 < num_tiles) td = a.descs[t0];
+    if (MODE == MODE_SEG && tk_a < num_tiles) td_a = a.descs[tk_a];
+    stage_tile(0, t0, td);
+  }
+  if (tid == 0) sm.skewed = 0;
+  if (MODE == MODE_RANGE && tid < MAX_PARTS) sm.split[tid] = (int)tid < a.num_parts - 1 ? a.splitters[tid] : 0xFFFFFFFFu;
+  __syncthreads();
+
+  for (uint32_t it = 0;; ++it) {
+    const int slot = (int)(it & 1u);
+    const TileGeom g = sm.geom[slot];
+    if (g.tile >= num_tiles) break;
+    if (tid == PRODUCER) {
+      stage_tile(slot ^ 1, tk_a, td_a);          // the other slot is free: its tile finished last iteration
+      tk_b = MODE != MODE_SEG ? atomicAdd(a.ticket, 1u) : tk_a + gridDim.x;
+      if (MODE == MODE_SEG && tk_b < num_tiles) td_b = a.descs[tk_b];
+    }
+    if (g.cnt == (uint32_t)TILE) scatter_tile<K, VB, THREADS, IPT, MODE, ORD, true>(a, sm, g, slot, num_tiles, it);
+    else scatter_tile<K, VB, THREADS, IPT, MODE, ORD, false>(a, sm, g, slot, num_tiles, it);
+    if (tid == PRODUCER) { tk_a = tk_b; td_a = td_b; }
+  }
+}
+
+}  // namespace b200

@@ -9,10 +9,11 @@
 //                   launch over every bucket that fits on chip.  All scheduling stays on the device.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include "hist.cuh"
 #include "local_sort.cuh"
 #include "msb_sched.cuh"
-#include "partition.cuh"
+#include "scatter.cuh"
 #include "sort_api.h"
 
 namespace b200 {
@@ -27,9 +28,9 @@ inline int num_sms() {
 
 template <typename K, int VB>
 struct Cfg {
-  // partition tile: 512 threads x (16 x u32 | 8 x u64) keys, two CTAs per SM
+  // scatter tile: 512 threads x IPT keys, sized so that two CTAs (double-buffered key + value staging, rank arrays) share an SM
   static constexpr int THREADS = 512;
-  static constexpr int IPT = (sizeof(K) == 4 && VB == 8) ? 8 : 64 / sizeof(K);
+  static constexpr int IPT = sizeof(K) == 4 ? (VB == 0 ? 16 : VB == 4 ? 8 : 5) : (VB == 0 ? 8 : VB == 4 ? 5 : 4);
   static constexpr int TILE = THREADS * IPT;
   // local sort: capacity = the largest bucket that is finished on chip (everything larger gets another level)
   static constexpr int LOCAL_THREADS = sizeof(K) == 4 ? 384 : (VB == 0 ? 768 : 512);
@@ -51,16 +52,16 @@ inline cudaError_t persistent_grid(KernelT kernel, int threads, size_t smem, int
   return cudaSuccess;
 }
 
-template <typename K, int VB, bool ORDERED>
-inline cudaError_t launch_partition(const PartArgs& a, uint32_t tiles_hint, cudaStream_t s) {
+template <typename K, int VB, int MODE, bool ORD>
+inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
-  auto kernel = partition_kernel<K, VB, C::THREADS, C::IPT, ORDERED>;
-  constexpr size_t smem = sizeof(PartSmem<K, VB, C::THREADS, C::IPT, ORDERED>);
-  static_assert(smem <= 227 * 1024, "partition tile exceeds the 227 KB shared-memory limit");
+  auto kernel = scatter_kernel<K, VB, C::THREADS, C::IPT, MODE, ORD>;
+  constexpr size_t smem = sizeof(ScatterSmem<K, VB, C::THREADS, C::IPT, MODE, ORD>);
+  static_assert(smem <= 113 * 1024, "two scatter CTAs must fit one SM's 228 KB of shared memory");
   static int grid = 0;
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
-  ProfScope prof(a.splitters ? "range_partition" : (ORDERED ? "partition_lsb" : "partition_msb"), s);
+  ProfScope prof(MODE == MODE_RANGE ? "range_partition" : (MODE == MODE_LSB ? "scatter_onesweep" : (ORD ? "scatter_stable" : "scatter")), s);
   kernel<<<g, C::THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
@@ -85,12 +86,11 @@ static __global__ void single_item_kernel(LocalItem* item, uint32_t* num_items, 
   *item = it; *num_items = 1; *ticket = 0;
 }
 // Zeroes the rows of the per-level arrays that the level will actually use.
-static __global__ void level_prep_kernel(uint32_t* seg_hist, const uint32_t* num_segs_ptr, uint32_t* status, const uint32_t* num_tiles_ptr) {
-  const uint64_t nh = (uint64_t)*num_segs_ptr * RADIX / 4, ns = (uint64_t)*num_tiles_ptr * RADIX / 4;
+static __global__ void level_prep_kernel(uint32_t* seg_hist, const uint32_t* num_segs_ptr) {
+  const uint64_t nh = (uint64_t)*num_segs_ptr * RADIX / 4;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint4 z = make_uint4(0, 0, 0, 0);
   for (uint64_t i = t; i < nh; i += stride) reinterpret_cast<uint4*>(seg_hist)[i] = z;
-  for (uint64_t i = t; i < ns; i += stride) reinterpret_cast<uint4*>(status)[i] = z;
 }
 
 struct Carver {      // sub-allocates the caller's temporary storage, 256-byte aligned
@@ -106,12 +106,138 @@ struct Carver {      // sub-allocates the caller's temporary storage, 256-byte a
 };
 
 // ===============================================================================================================
-// Stable LSB sort.
-// keys[0]/vals[0] = current (input), keys[1]/vals[1] = alternate.  *selector (out) = which one holds the result.
+// The MSD engine shared by both entry points: per level [tile histograms -> group carry -> classify -> scatter ->
+// next level's tile list], then ONE on-chip sort launch over every bucket that fits a CTA's shared memory.
+//   ORDERED = false : unstable (MSB hybrid sort, rdxsrt_unstable_sort): atomic in-tile ranking, one-shot counting local sort
+//   ORDERED = true  : stable (the cub::DeviceRadixSort contract): match-based in-tile ranking, stable LSD local sort.
+// Tiles never wait for each other: a tile's destination = sub-bucket start + counts of earlier tiles, all known before
+// the scatter starts, so placement is deterministic and (with stable ranking) the whole sort is stable.
+// bufk/bufv: up to three ping-pong buffers; buffer 0 holds the input; level L scatters into out_of_level(L); buckets are
+// finished into buffer `fin`.  Sorts on bits [begin_bit, end_bit) of the transformed key.  n < 2^32.
+// ===============================================================================================================
+struct MsdWorkspace {
+  MsbCounters* ctr; Seg* segs0; Seg* segs1; uint32_t* tile_base; TileDesc* descs; uint32_t* seg_hist; uint64_t* bins;
+  uint32_t* tile_off; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals;
+  uint32_t max_segs, max_tiles, max_locals, max_groups;
+};
+
+template <typename K, int VB>
+inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
+  using C = Cfg<K, VB>;
+  constexpr int LEVELS = sizeof(K);
+  w.max_segs = (uint32_t)(n / C::LOCAL_CAP) + 2;
+  w.max_tiles = (uint32_t)(n / C::TILE) + w.max_segs + 1;
+  w.max_groups = w.max_tiles / HIST_GROUP + 1;
+  w.max_locals = (uint32_t)std::min<uint64_t>(4 * n / C::MERGE_CAP + 4ull * LEVELS * w.max_segs + 16, 0x7fffffffu);
+  w.ctr = cv.take<MsbCounters>(1);
+  w.segs0 = cv.take<Seg>(w.max_segs);
+  w.segs1 = cv.take<Seg>(w.max_segs);
+  w.tile_base = cv.take<uint32_t>(w.max_segs + 1);
+  w.descs = cv.take<TileDesc>(w.max_tiles);
+  w.seg_hist = cv.take<uint32_t>((size_t)w.max_segs * RADIX);
+  w.bins = cv.take<uint64_t>((size_t)w.max_segs * RADIX);
+  w.tile_off = cv.take<uint32_t>((size_t)w.max_tiles * RADIX);
+  w.group_tail = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
+  w.group_flag = cv.take<uint32_t>(w.max_groups);
+  w.carry = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
+  w.locals = cv.take<LocalItem>(w.max_locals);
+}
+
+template <typename K, int VB, bool ORDERED>
+cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const bufv[3], int nbuf, int fin, uint64_t n, const Twiddle& tw,
+                         int begin_bit, int end_bit, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  const int levels = (end_bit - begin_bit + 7) / 8;
+  const int sms = num_sms();
+  MsbCounters* ctr = w.ctr;
+  // level L scatters from in_buf(L) to out_buf(L); the LAST possible level must land in `fin`
+  auto out_buf = [&](int L) -> int {
+    if (nbuf == 2) return (L + 1) & 1;
+    return ((levels - 1 - L) & 1) == 0 ? fin : (fin == 1 ? 2 : 1);      // never the input buffer 0
+  };
+  auto in_buf = [&](int L) -> int { return L == 0 ? 0 : out_buf(L - 1); };
+
+  LocalArgs la{};
+  for (int i = 0; i < 3; ++i) { la.keys[i] = bufk[i < nbuf ? i : 0]; la.vals[i] = bufv[i < nbuf ? i : 0]; }
+  la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
+  la.items = w.locals; la.num_items_ptr = &ctr->num_locals;
+  la.tw_out = 1; la.stable = ORDERED ? 1 : 0; la.begin_bit = begin_bit; la.tw = tw;
+
+  if (n <= (uint64_t)C::LOCAL_CAP) {     // fits one CTA: a single on-chip sort straight into the final buffer
+    single_item_kernel<<<1, 1, 0, s>>>(w.locals, &ctr->num_locals, &ctr->local_ticket, (uint32_t)n, end_bit);
+    la.tw_in = 1;
+    return launch_local<K, VB>(la, 1, s);
+  }
+
+  B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
+  {
+    ProfScope prof("msb_sched", s);
+    msb_init_kernel<<<1, 32, 0, s>>>(w.segs0, ctr, n);
+    scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(w.segs0, &ctr->num_segs[0], w.tile_base, &ctr->num_tiles[0], w.max_tiles, &ctr->error, C::TILE);
+    fill_descs_kernel<<<sms * 2, 256, 0, s>>>(w.segs0, w.tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], w.descs, C::TILE);
+  }
+  for (int L = 0; L < levels; ++L) {
+    const int shift = std::max(begin_bit, end_bit - 8 * (L + 1));
+    const int nb = (end_bit - 8 * L) - shift;
+    const uint32_t mask = (1u << nb) - 1u;
+    Seg* cur = (L & 1) ? w.segs1 : w.segs0;
+    Seg* nxt = (L & 1) ? w.segs0 : w.segs1;
+    const int ib = in_buf(L), ob = out_buf(L);
+
+    { ProfScope prof("msb_sched", s); level_prep_kernel<<<sms * 2, 512, 0, s>>>(w.seg_hist, &ctr->num_segs[L]); }
+    TileHistArgs ha{};
+    ha.keys = bufk[ib]; ha.descs = w.descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
+    ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist;
+    ha.shift = shift; ha.mask = mask; ha.tw_in = (L == 0); ha.tw = tw;
+    const int hgrid = (int)std::min<uint32_t>(w.max_groups, (uint32_t)sms * 4);
+    { ProfScope prof("tile_hist", s); tile_hist_kernel<K><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
+    { ProfScope prof("msb_sched", s); group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(w.group_tail, w.group_flag, w.carry, &ctr->num_tiles[L]); }
+
+    ClassifyArgs ca{};
+    ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = w.seg_hist; ca.bins = w.bins;
+    ca.next_segs = nxt; ca.num_next_ptr = &ctr->num_segs[L + 1]; ca.max_segs = w.max_segs;
+    ca.locals = w.locals; ca.num_locals_ptr = &ctr->num_locals; ca.max_locals = w.max_locals;
+    ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
+    ca.local_cap = C::LOCAL_CAP; ca.merge_cap = C::MERGE_CAP;
+    ca.out_buf = (uint32_t)ob;
+    const int cgrid = (int)std::min<uint32_t>((w.max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
+    { ProfScope prof("msb_sched", s); classify_kernel<<<L == 0 ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca); }
+
+    ScatterArgs pa{};
+    pa.keys_in = bufk[ib]; pa.keys_out = bufk[ob]; pa.vals_in = bufv[ib]; pa.vals_out = bufv[ob];
+    pa.descs = w.descs; pa.num_tiles_ptr = &ctr->num_tiles[L];
+    pa.bins = w.bins; pa.tile_off = w.tile_off; pa.carry = w.carry;
+    pa.shift = shift; pa.mask = mask; pa.tw_in = (L == 0); pa.tw_out = (shift == begin_bit); pa.tw = tw;
+    B200_CHECK((launch_scatter<K, VB, MODE_SEG, ORDERED>(pa, w.max_tiles, s)));
+
+    if (L + 1 < levels) {
+      ProfScope prof("msb_sched", s);
+      scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(nxt, &ctr->num_segs[L + 1], w.tile_base, &ctr->num_tiles[L + 1], w.max_tiles, &ctr->error, C::TILE);
+      fill_descs_kernel<<<sms * 2, 256, 0, s>>>(nxt, w.tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], w.descs, C::TILE);
+    }
+  }
+  la.tw_in = 0;
+  B200_CHECK((launch_local<K, VB>(la, w.max_locals, s)));
+  return cudaGetLastError();
+}
+
+// ===============================================================================================================
+// Stable sort behind the cub::DeviceRadixSort call shape.
+// k0/v0 = current (input), k1/v1 = alternate.  *selector (out) = which one holds the result.
 // allow_overwrite = 0: the input buffers are left untouched and the result is delivered in the alternate buffers
 // (CUB's pointer overloads, device_radix_sort.cuh:147-179; needs a third buffer inside the temporary storage,
 // dispatch_radix_sort.cuh:1099-1104).
+// Engine: the stable MSD hybrid above (fewer sweeps than one-pass-per-digit LSD whenever the leading digits split
+// the keys: hist + 2 scatters + 1 on-chip sweep for 2^28 uniform keys of ANY width).  The onesweep LSD engine
+// (one up-front histogram, one look-back scatter per digit) is kept: B200SORT_LSB_ENGINE=onesweep selects it, and it
+// serves n >= 2^32.  Both are stable, so their results are identical bit for bit.
 // ===============================================================================================================
+inline bool use_onesweep_engine() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200SORT_LSB_ENGINE"); v = (e && e[0] == 'o') ? 1 : 0; }
+  return v == 1;
+}
+
 template <typename K, int VB>
 cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, void* v0, void* v1, int* selector,
                           uint64_t n, const Twiddle& tw, int begin_bit, int end_bit, int allow_overwrite, cudaStream_t s) {
@@ -121,16 +247,23 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
   if (begin_bit < 0) begin_bit = 0;
   if (end_bit > KEY_BITS) end_bit = KEY_BITS;
   const int passes = end_bit > begin_bit ? (end_bit - begin_bit + 7) / 8 : 0;
+  const bool onesweep = use_onesweep_engine() || n >= (1ull << 32);
   const uint64_t portion = (MAX_PORTION / C::TILE) * C::TILE;
   const uint64_t max_tiles = (std::min<uint64_t>(n, portion) + C::TILE - 1) / C::TILE;
   const bool need_third = !allow_overwrite && passes > 1 && n > (uint64_t)C::LOCAL_CAP;
 
   Carver cv(d_temp);
-  unsigned long long* hist = cv.take<unsigned long long>((size_t)MAX_PASSES * RADIX);
-  uint64_t* pbins = cv.take<uint64_t>(2 * RADIX);
-  uint32_t* tick_status = cv.take<uint32_t>(64 + max_tiles * RADIX);     // [ticket | pad | status...], one memset clears both
-  LocalItem* one_item = cv.take<LocalItem>(1);
-  uint32_t* one_count = cv.take<uint32_t>(2);
+  MsdWorkspace w{};
+  unsigned long long* hist = nullptr; uint64_t* pbins = nullptr; uint32_t* tick_status = nullptr;
+  if (onesweep) {
+    hist = cv.take<unsigned long long>((size_t)MAX_PASSES * RADIX);
+    pbins = cv.take<uint64_t>(2 * RADIX);
+    tick_status = cv.take<uint32_t>(64 + max_tiles * RADIX);     // [ticket | pad | status...], one memset clears both
+    w.ctr = cv.take<MsbCounters>(1);
+    w.locals = cv.take<LocalItem>(1);
+  } else {
+    msd_carve<K, VB>(cv, n, w);
+  }
   K* k2 = need_third ? cv.take<K>(n) : nullptr;
   V* v2 = (need_third && VB) ? cv.take<V>(n) : nullptr;
   if (d_temp == nullptr) { *temp_bytes = std::max<size_t>(cv.total(), 256); return cudaSuccess; }
@@ -146,20 +279,16 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     }
     return cudaSuccess;
   }
-
-  if (n <= (uint64_t)C::LOCAL_CAP) {     // single tile: one on-chip sort, result in the alternate buffer
-    single_item_kernel<<<1, 1, 0, s>>>(one_item, one_count, one_count + 1, (uint32_t)n, end_bit);
-    LocalArgs la{};
-    la.keys[0] = k0; la.keys[1] = k0; la.vals[0] = v0; la.vals[1] = v0;
-    la.keys_final = k1; la.vals_final = v1;
-    la.items = one_item; la.num_items_ptr = one_count;
-    la.tw_in = 1; la.tw_out = 1; la.stable = 1; la.begin_bit = begin_bit; la.tw = tw;
-    B200_CHECK((launch_local<K, VB>(la, 1, s)));
-    if (selector) *selector = 1;
-    return cudaSuccess;
+  if (!onesweep || n <= (uint64_t)C::LOCAL_CAP) {
+    void* bufk[3] = {k0, k1, k2}; void* bufv[3] = {v0, v1, v2};
+    // two buffers: the last possible level lands in buffer (passes & 1), so that is where everything is finished
+    // (DoubleBuffer semantics: the selector says where); pointer overloads always deliver into the alternate buffers
+    const int fin = (allow_overwrite && n > (uint64_t)C::LOCAL_CAP) ? (passes & 1) : 1;
+    if (selector) *selector = fin;
+    return msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, fin, n, tw, begin_bit, end_bit, s);
   }
 
-  // ---- all digit histograms in one read, then digit starts
+  // ---- onesweep LSD engine: all digit histograms in one read, then one look-back scatter launch per digit
   B200_CHECK(cudaMemsetAsync(hist, 0, (size_t)passes * RADIX * sizeof(unsigned long long), s));
   {
     HistAllArgs ha{};
@@ -169,8 +298,6 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     { ProfScope prof("hist_all", s); hist_all_kernel<K><<<grid, HIST_THREADS, 0, s>>>(ha); }
     { ProfScope prof("scan_bins", s); scan_bins_kernel<<<passes, RADIX, 0, s>>>(hist, 0); }
   }
-
-  // ---- one partition launch per digit (per portion of < 2^30 keys)
   const void* src_k = k0; const void* src_v = v0;
   for (int p = 0; p < passes; ++p) {
     void* dst_k; void* dst_v;
@@ -183,16 +310,16 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
       const uint64_t pn = std::min<uint64_t>(portion, n - base);
       const uint32_t tiles = (uint32_t)((pn + C::TILE - 1) / C::TILE);
       B200_CHECK(cudaMemsetAsync(tick_status, 0, (64 + (size_t)tiles * RADIX) * sizeof(uint32_t), s));
-      PartArgs pa{};
+      ScatterArgs pa{};
       pa.keys_in = src_k; pa.keys_out = dst_k; pa.vals_in = src_v; pa.vals_out = dst_v;
       pa.descs = nullptr; pa.num_tiles_ptr = nullptr;
       pa.num_tiles = tiles; pa.base = base; pa.n = pn;
-      pa.bins = (q == 0) ? reinterpret_cast<const uint64_t*>(hist + (size_t)p * RADIX) : pbins + ((q - 1) & 1) * RADIX;
+      pa.bins = (q == 0) ? reinterpret_cast<uint64_t*>(hist + (size_t)p * RADIX) : pbins + ((q - 1) & 1) * RADIX;
       pa.bins_next = (base + pn < n) ? pbins + (q & 1) * RADIX : nullptr;
       pa.status = tick_status + 64; pa.ticket = tick_status;
       pa.shift = shift; pa.mask = (1u << nb) - 1u;
       pa.tw_in = (p == 0); pa.tw_out = (p == passes - 1); pa.tw = tw;
-      B200_CHECK((launch_partition<K, VB, true>(pa, tiles, s)));
+      B200_CHECK((launch_scatter<K, VB, MODE_LSB, true>(pa, tiles, s)));
     }
     src_k = dst_k; src_v = dst_v;
   }
@@ -207,109 +334,28 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
 template <typename K, int VB>
 cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, void* vals_alt, const Twiddle& tw,
                           void* d_ws, size_t* ws_bytes, cudaStream_t s, void** out_keys, void** out_vals) {
-  using C = Cfg<K, VB>;
   constexpr int KEY_BITS = sizeof(K) * 8;
   constexpr int LEVELS = sizeof(K);
   if (out_keys) *out_keys = keys;
   if (out_vals) *out_vals = vals;
 
-  if (n > MAX_PORTION) {     // beyond the 30-bit look-back range: the stable LSB path gives a valid result
+  if (n >= (1ull << 32)) {     // beyond the 32-bit tile offsets: the stable LSD engine gives a valid result
     int sel = 0;
     cudaError_t e = lsb_sort_impl<K, VB>(d_ws, ws_bytes, keys, keys_alt, vals, vals_alt, &sel, n, tw, 0, KEY_BITS, 1, s);
     if (d_ws && e == cudaSuccess && sel) { if (out_keys) *out_keys = keys_alt; if (out_vals) *out_vals = vals_alt; }
     return e;
   }
-
-  const uint32_t max_segs = (uint32_t)(n / C::LOCAL_CAP) + 2;
-  const uint32_t max_tiles = (uint32_t)(n / C::TILE) + max_segs + 1;
-  const uint32_t max_locals = (uint32_t)std::min<uint64_t>(4 * n / C::MERGE_CAP + 4ull * LEVELS * max_segs + 16, 0x7fffffffu);
-
   Carver cv(d_ws);
-  MsbCounters* ctr = cv.take<MsbCounters>(1);
-  Seg* segs0 = cv.take<Seg>(max_segs);
-  Seg* segs1 = cv.take<Seg>(max_segs);
-  uint32_t* tile_base = cv.take<uint32_t>(max_segs + 1);
-  TileDesc* descs = cv.take<TileDesc>(max_tiles);
-  uint32_t* seg_hist = cv.take<uint32_t>((size_t)max_segs * RADIX);
-  uint64_t* bins = cv.take<uint64_t>((size_t)max_segs * RADIX);
-  uint32_t* status = cv.take<uint32_t>((size_t)max_tiles * RADIX);
-  LocalItem* locals = cv.take<LocalItem>(max_locals);
+  MsdWorkspace w{};
+  msd_carve<K, VB>(cv, n, w);
   if (d_ws == nullptr) { *ws_bytes = std::max<size_t>(cv.total(), 256); return cudaSuccess; }
   if (*ws_bytes < cv.total()) return cudaErrorInvalidValue;
   if (n == 0) return cudaSuccess;
-
-  void* kbuf[2] = {keys, keys_alt};
-  void* vbuf[2] = {vals, vals_alt};
-  void* kfin = kbuf[LEVELS & 1];
-  void* vfin = vbuf[LEVELS & 1];
-  if (out_keys) *out_keys = kfin;
-  if (out_vals) *out_vals = vfin;
-  const int sms = num_sms();
-
-  if (n <= (uint64_t)C::LOCAL_CAP) {   // fits one CTA: a single on-chip sort, in place
-    single_item_kernel<<<1, 1, 0, s>>>(locals, &ctr->num_locals, &ctr->local_ticket, (uint32_t)n, KEY_BITS);
-    LocalArgs la{};
-    la.keys[0] = keys; la.keys[1] = keys; la.vals[0] = vals; la.vals[1] = vals;
-    la.keys_final = kfin; la.vals_final = vfin;
-    la.items = locals; la.num_items_ptr = &ctr->num_locals;
-    la.tw_in = 1; la.tw_out = 1; la.stable = 0; la.begin_bit = 0; la.tw = tw;
-    if (kfin != keys) {   // odd level counts (not reachable for 4/8-byte keys): sort into the other buffer
-      la.keys_final = kfin; la.vals_final = vfin;
-    }
-    return launch_local<K, VB>(la, 1, s);
-  }
-
-  B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
-  {
-    ProfScope prof("msb_sched", s);
-    msb_init_kernel<<<1, 32, 0, s>>>(segs0, ctr, n);
-    scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(segs0, &ctr->num_segs[0], tile_base, &ctr->num_tiles[0], max_tiles, &ctr->error, C::TILE);
-    fill_descs_kernel<<<sms * 2, 256, 0, s>>>(segs0, tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], descs, C::TILE);
-  }
-
-  for (int L = 0; L < LEVELS; ++L) {
-    const int shift = KEY_BITS - 8 * (L + 1);
-    Seg* cur = (L & 1) ? segs1 : segs0;
-    Seg* nxt = (L & 1) ? segs0 : segs1;
-    const void* in_k = kbuf[L & 1]; void* out_k = kbuf[(L + 1) & 1];
-    const void* in_v = vbuf[L & 1]; void* out_v = vbuf[(L + 1) & 1];
-
-    { ProfScope prof("msb_sched", s); level_prep_kernel<<<sms * 2, 512, 0, s>>>(seg_hist, &ctr->num_segs[L], status, &ctr->num_tiles[L]); }
-    SegHistArgs ha{};
-    ha.keys = in_k; ha.segs = cur; ha.descs = descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
-    ha.seg_hist = seg_hist; ha.tile = C::TILE; ha.shift = shift; ha.tw_in = (L == 0); ha.tw = tw;
-    { ProfScope prof("seg_hist", s); seg_hist_kernel<K><<<sms * 4, HIST_THREADS, 0, s>>>(ha); }
-
-    ClassifyArgs ca{};
-    ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = seg_hist; ca.bins = bins;
-    ca.next_segs = nxt; ca.num_next_ptr = &ctr->num_segs[L + 1]; ca.max_segs = max_segs;
-    ca.locals = locals; ca.num_locals_ptr = &ctr->num_locals; ca.max_locals = max_locals;
-    ca.error = &ctr->error; ca.shift = shift; ca.local_cap = C::LOCAL_CAP; ca.merge_cap = C::MERGE_CAP;
-    ca.out_buf = (uint32_t)((L + 1) & 1);
-    const int cgrid = (int)std::min<uint32_t>((max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
-    { ProfScope prof("msb_sched", s); classify_kernel<<<L == 0 ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca); }
-
-    PartArgs pa{};
-    pa.keys_in = in_k; pa.keys_out = out_k; pa.vals_in = in_v; pa.vals_out = out_v;
-    pa.descs = descs; pa.num_tiles_ptr = &ctr->num_tiles[L];
-    pa.bins = bins; pa.bins_next = nullptr; pa.status = status; pa.ticket = &ctr->part_ticket[L];
-    pa.shift = shift; pa.mask = 0xFFu; pa.tw_in = (L == 0); pa.tw_out = (shift == 0); pa.tw = tw;
-    B200_CHECK((launch_partition<K, VB, false>(pa, max_tiles, s)));
-
-    if (L + 1 < LEVELS) {
-      ProfScope prof("msb_sched", s);
-      scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(nxt, &ctr->num_segs[L + 1], tile_base, &ctr->num_tiles[L + 1], max_tiles, &ctr->error, C::TILE);
-      fill_descs_kernel<<<sms * 2, 256, 0, s>>>(nxt, tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], descs, C::TILE);
-    }
-  }
-
-  LocalArgs la{};
-  la.keys[0] = kbuf[0]; la.keys[1] = kbuf[1]; la.vals[0] = vbuf[0]; la.vals[1] = vbuf[1];
-  la.keys_final = kfin; la.vals_final = vfin;
-  la.items = locals; la.num_items_ptr = &ctr->num_locals;
-  la.tw_in = 0; la.tw_out = 1; la.stable = 0; la.begin_bit = 0; la.tw = tw;
-  B200_CHECK((launch_local<K, VB>(la, max_locals, s)));
-  return cudaGetLastError();
+  void* bufk[3] = {keys, keys_alt, nullptr}; void* bufv[3] = {vals, vals_alt, nullptr};
+  const int fin = LEVELS & 1;               // 4 / 8 levels: the last level lands in the input buffer, like the reference
+  if (out_keys) *out_keys = bufk[fin];
+  if (out_vals) *out_vals = bufv[fin];
+  return msd_sort_run<K, VB, false>(w, bufk, bufv, 2, fin, n, tw, 0, KEY_BITS, s);
 }
 
 // ===============================================================================================================
@@ -363,7 +409,7 @@ cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* k
     const uint64_t pn = std::min<uint64_t>(portion, n - base);
     const uint32_t tiles = (uint32_t)((pn + C::TILE - 1) / C::TILE);
     B200_CHECK(cudaMemsetAsync(tick_status, 0, (64 + (size_t)tiles * RADIX) * sizeof(uint32_t), s));
-    PartArgs pa{};
+    ScatterArgs pa{};
     pa.keys_in = kin; pa.keys_out = kout; pa.vals_in = vin; pa.vals_out = vout;
     pa.num_tiles = tiles; pa.base = base; pa.n = pn;
     pa.bins = (q == 0) ? bins : pbins + ((q - 1) & 1) * RADIX;
@@ -372,7 +418,7 @@ cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* k
     pa.shift = KEY_BITS - bits; pa.mask = (uint32_t)(num_parts - 1);
     pa.tw_in = 1; pa.tw_out = 1; pa.tw = tw;
     pa.splitters = d_splitters; pa.num_parts = num_parts;
-    B200_CHECK((launch_partition<K, VB, true>(pa, tiles, s)));
+    B200_CHECK((launch_scatter<K, VB, MODE_RANGE, true>(pa, tiles, s)));
   }
   return cudaGetLastError();
 }
