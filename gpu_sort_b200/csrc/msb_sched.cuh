@@ -17,8 +17,8 @@ struct MsbCounters {            // one small zero-initialised block in the works
   uint32_t num_segs[10];        // per level
   uint32_t num_tiles[10];
   uint32_t part_ticket[10];
-  uint32_t num_locals;
-  uint32_t local_ticket;
+  uint32_t num_locals[2];       // work lists of the two on-chip sort algorithms (ALGO_LSD, ALGO_COUNT)
+  uint32_t num_overflow;        // buckets the counting sort handed back
   uint32_t error;
   uint32_t pad;
 };

@@ -66,24 +66,24 @@ inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cud
   return cudaGetLastError();
 }
 
-template <typename K, int VB>
+template <typename K, int VB, int ALGO, bool STABLE>
 inline cudaError_t launch_local(const LocalArgs& a, uint32_t items_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
-  auto kernel = local_sort_kernel<K, VB, C::LOCAL_THREADS, C::LOCAL_IPT>;
-  constexpr size_t smem = sizeof(LocalSmem<K, VB, C::LOCAL_THREADS, C::LOCAL_IPT>);
+  auto kernel = local_sort_kernel<K, VB, C::LOCAL_THREADS, C::LOCAL_IPT, ALGO, STABLE>;
+  constexpr size_t smem = sizeof(LocalSmem<K, VB, C::LOCAL_THREADS, C::LOCAL_IPT, ALGO>);
   static_assert(smem <= 227 * 1024, "local sort exceeds the 227 KB shared-memory limit");
   static int grid = 0;
   if (!grid) B200_CHECK(persistent_grid(kernel, C::LOCAL_THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
-  ProfScope prof("local_sort", s);
+  ProfScope prof(ALGO == ALGO_LSD ? "local_sort_lsd" : "local_sort_count", s);
   kernel<<<g, C::LOCAL_THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
 
 // Tiny helper kernels --------------------------------------------------------------------------------------------
-static __global__ void single_item_kernel(LocalItem* item, uint32_t* num_items, uint32_t* ticket, uint32_t cnt, int nbits) {
+static __global__ void single_item_kernel(LocalItem* item, uint32_t* num_items, uint32_t cnt, int nbits) {
   LocalItem it; it.off = 0; it.cnt = cnt; it.nbits = (uint16_t)nbits; it.src = 0;
-  *item = it; *num_items = 1; *ticket = 0;
+  *item = it; *num_items = 1;
 }
 // Zeroes the rows of the per-level arrays that the level will actually use.
 static __global__ void level_prep_kernel(uint32_t* seg_hist, const uint32_t* num_segs_ptr) {
@@ -117,7 +117,7 @@ struct Carver {      // sub-allocates the caller's temporary storage, 256-byte a
 // ===============================================================================================================
 struct MsdWorkspace {
   MsbCounters* ctr; Seg* segs0; Seg* segs1; uint32_t* tile_base; TileDesc* descs; uint32_t* seg_hist; uint64_t* bins;
-  uint32_t* tile_off; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals;
+  uint32_t* tile_off; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[3];   // LSD list, counting list, overflow
   uint32_t max_segs, max_tiles, max_locals, max_groups;
 };
 
@@ -140,7 +140,7 @@ inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
   w.group_tail = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
   w.group_flag = cv.take<uint32_t>(w.max_groups);
   w.carry = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
-  w.locals = cv.take<LocalItem>(w.max_locals);
+  for (int i = 0; i < 3; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
 }
 
 template <typename K, int VB, bool ORDERED>
@@ -160,13 +160,14 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   LocalArgs la{};
   for (int i = 0; i < 3; ++i) { la.keys[i] = bufk[i < nbuf ? i : 0]; la.vals[i] = bufv[i < nbuf ? i : 0]; }
   la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
-  la.items = w.locals; la.num_items_ptr = &ctr->num_locals;
-  la.tw_out = 1; la.stable = ORDERED ? 1 : 0; la.begin_bit = begin_bit; la.tw = tw;
+  la.items = w.locals[0]; la.num_items_ptr = &ctr->num_locals[0];
+  la.overflow = w.locals[2]; la.num_overflow_ptr = &ctr->num_overflow;
+  la.tw_out = 1; la.begin_bit = begin_bit; la.tw = tw;
 
   if (n <= (uint64_t)C::LOCAL_CAP) {     // fits one CTA: a single on-chip sort straight into the final buffer
-    single_item_kernel<<<1, 1, 0, s>>>(w.locals, &ctr->num_locals, &ctr->local_ticket, (uint32_t)n, end_bit);
+    single_item_kernel<<<1, 1, 0, s>>>(w.locals[0], &ctr->num_locals[0], (uint32_t)n, end_bit);
     la.tw_in = 1;
-    return launch_local<K, VB>(la, 1, s);
+    return launch_local<K, VB, ALGO_LSD, ORDERED>(la, 1, s);
   }
 
   B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
@@ -196,7 +197,9 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     ClassifyArgs ca{};
     ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = w.seg_hist; ca.bins = w.bins;
     ca.next_segs = nxt; ca.num_next_ptr = &ctr->num_segs[L + 1]; ca.max_segs = w.max_segs;
-    ca.locals = w.locals; ca.num_locals_ptr = &ctr->num_locals; ca.max_locals = w.max_locals;
+    int list = (shift - begin_bit > 16) ? ALGO_COUNT : ALGO_LSD;     // buckets of this level: which on-chip algorithm
+    { static const char* e = getenv("B200SORT_LOCAL"); if (e) list = (e[0] == 'c') ? ALGO_COUNT : ALGO_LSD; }
+    ca.locals = w.locals[list]; ca.num_locals_ptr = &ctr->num_locals[list]; ca.max_locals = w.max_locals;
     ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
     ca.local_cap = C::LOCAL_CAP; ca.merge_cap = C::MERGE_CAP;
     ca.out_buf = (uint32_t)ob;
@@ -217,7 +220,13 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     }
   }
   la.tw_in = 0;
-  B200_CHECK((launch_local<K, VB>(la, w.max_locals, s)));
+  B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
+  if (end_bit - begin_bit > 24) {          // some level left more than 16 bits to its buckets
+    la.items = w.locals[ALGO_COUNT]; la.num_items_ptr = &ctr->num_locals[ALGO_COUNT];
+    B200_CHECK((launch_local<K, VB, ALGO_COUNT, ORDERED>(la, w.max_locals, s)));
+    la.items = w.locals[2]; la.num_items_ptr = &ctr->num_overflow;       // buckets with overfull cells: LSD passes instead
+    B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
+  }
   return cudaGetLastError();
 }
 
@@ -260,7 +269,7 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     pbins = cv.take<uint64_t>(2 * RADIX);
     tick_status = cv.take<uint32_t>(64 + max_tiles * RADIX);     // [ticket | pad | status...], one memset clears both
     w.ctr = cv.take<MsbCounters>(1);
-    w.locals = cv.take<LocalItem>(1);
+    w.locals[0] = cv.take<LocalItem>(1);
   } else {
     msd_carve<K, VB>(cv, n, w);
   }
