@@ -34,7 +34,7 @@ WORKLOADS = {
     # name: (log2 n, key bits, value bytes, path, dist, param, algorithmic full sweeps S, description)
     "cfg1": (24, 32, 0, "msb", "uniform", 0, 3, "2^24 uniform uint32 keys, keys-only, MSB hybrid"),
     "cfg2": (28, 32, 0, "msb", "uniform", 0, 3, "2^28 uniform uint32 keys, keys-only, MSB hybrid radix sort"),
-    "cfg3": (28, 32, 4, "lsb", "uniform", 0, 4, "2^28 uint32 key + uint32 value pairs, stable LSB sort"),
+    "cfg3": (28, 32, 4, "lsb", "uniform", 0, 3, "2^28 uint32 key + uint32 value pairs, stable sort (cub::DeviceRadixSort call shape)"),
     "cfg4": (29, 64, 0, "msb", "zipf_hash", 0, 3, "2^29 uint64 keys, Zipf-skewed, MSB hybrid"),
 }
 
@@ -187,18 +187,17 @@ def run_ours_single(args, wl):
     dom_name, (dom_cnt, dom_ms) = dom
     kbytes, vbytes = kbits // 8, vb
     sweep_bytes = 2 * n * (kbytes + vbytes)
-    # algorithmic bytes of the dominant kernel per step (DESIGN.md "Kernels"): the scatter kernels move every key once per
-    # sweep they run (read + write); the on-chip local sort likewise (one read + one write of every key).
-    if dom_name in ("partition_msb", "partition_lsb"):
-        sweeps = (S - 1) if path == "msb" else S
-    else:
-        sweeps = 1
-    dom_bytes = sweeps * sweep_bytes
+    # algorithmic bytes of the dominant kernel family per step (DESIGN.md "Kernels"): S - 1 scatter sweeps each read and
+    # write every key (+ value) once; each is preceded by one histogram read of the keys; the on-chip sort reads and writes
+    # every key (+ value) once.  Both entry points run the same MSD engine (stable or not).
+    fam_bytes = {"scatter": (S - 1) * sweep_bytes, "scatter_stable": (S - 1) * sweep_bytes, "scatter_onesweep": S * sweep_bytes,
+                 "tile_hist": (S - 1) * n * kbytes, "hist_all": n * kbytes, "local_sort_lsd": sweep_bytes, "local_sort_count": sweep_bytes}
+    dom_bytes = fam_bytes.get(dom_name, sweep_bytes)
     dom_ms_per_step = dom_ms / args.steps
     peak, peak_src = peaks()
     achieved = dom_bytes / (dom_ms_per_step * 1e-3) / 1e9
     med = float(np.median(ms)); mean = float(np.mean(ms))
-    whole_bytes = n * kbytes + S * sweep_bytes
+    whole_bytes = n * kbytes + S * sweep_bytes       # the contract figure of SURVEY.md section 8(d): one histogram read + S sweeps
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": round(dom_ms_per_step, 4),

@@ -126,10 +126,21 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
       const uint32_t head = min(cnt, mis ? VEC - mis : 0u);
       const uint32_t nvec = (cnt - head) / VEC;
       const uint4* pv = reinterpret_cast<const uint4*>(p + head);
-      for (uint32_t i = tid; i < nvec; i += HIST_THREADS) {
-        const uint4 q = pv[i];
-        if (sizeof(K) == 4) { count((K)q.x); count((K)q.y); count((K)q.z); count((K)q.w); }
-        else { count((K)(((uint64_t)q.y << 32) | q.x)); count((K)(((uint64_t)q.w << 32) | q.z)); }
+      // batches of four independent 16-byte loads per thread before any counting (memory-level parallelism)
+      for (uint32_t i0 = 0; i0 < nvec; i0 += 4 * HIST_THREADS) {
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = i0 + u * HIST_THREADS + tid;
+          q[u] = i < nvec ? pv[i] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i0 + u * HIST_THREADS + tid < nvec) {
+            if (sizeof(K) == 4) { count((K)q[u].x); count((K)q[u].y); count((K)q[u].z); count((K)q[u].w); }
+            else { count((K)(((uint64_t)q[u].y << 32) | q[u].x)); count((K)(((uint64_t)q[u].w << 32) | q[u].z)); }
+          }
+        }
       }
       if (tid < head) count(p[tid]);
       const uint32_t tail0 = head + nvec * VEC;

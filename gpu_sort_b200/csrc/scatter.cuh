@@ -371,14 +371,14 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
   }
 }
 
-template <typename K, int VB, int THREADS, int IPT, int MODE, bool ORD>
-__global__ void __launch_bounds__(THREADS, 2) scatter_kernel(const __grid_constant__ ScatterArgs a) {
+template <typename K, int VB, int THREADS, int IPT, int OCC, int MODE, bool ORD>
+__global__ void __launch_bounds__(THREADS, OCC) scatter_kernel(const __grid_constant__ ScatterArgs a) {
   using SM = ScatterSmem<K, VB, THREADS, IPT, MODE, ORD>;
   using V = typename SM::V;
   constexpr int TILE = SM::TILE;
   constexpr bool ORDERED = SM::ORDERED;
-  constexpr unsigned PRODUCER = THREADS - 1;     // not a digit owner (THREADS > 256)
-  static_assert(THREADS > RADIX, "producer thread must not own a digit");
+  constexpr unsigned PRODUCER = THREADS - 1;
+  static_assert(THREADS >= RADIX, "one digit owner per digit");
   static_assert(TILE < 65536, "per-warp start positions are 16-bit");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);

@@ -29,12 +29,26 @@ inline int num_sms() {
 template <typename K, int VB>
 struct Cfg {
   // scatter tile: 512 threads x IPT keys, sized so that two CTAs (double-buffered key + value staging, rank arrays) share an SM
-  static constexpr int THREADS = 512;
-  static constexpr int IPT = sizeof(K) == 4 ? (VB == 0 ? 16 : VB == 4 ? 8 : 5) : (VB == 0 ? 8 : VB == 4 ? 5 : 4);
+#ifndef B200_SCATTER_THREADS
+#define B200_SCATTER_THREADS 512
+#endif
+#ifndef B200_IPT_NUM
+#define B200_IPT_NUM 1
+#define B200_IPT_DEN 1
+#endif
+#ifndef B200_LOCAL_IPT32
+#define B200_LOCAL_IPT32 12
+#endif
+  static constexpr int THREADS = B200_SCATTER_THREADS;
+  static constexpr int IPT = (sizeof(K) == 4 ? (VB == 0 ? 16 : VB == 4 ? 8 : 5) : (VB == 0 ? 8 : VB == 4 ? 5 : 4)) * B200_IPT_NUM / B200_IPT_DEN;
+#ifndef B200_SCATTER_OCC
+#define B200_SCATTER_OCC (1024 / B200_SCATTER_THREADS)
+#endif
+  static constexpr int OCC = B200_SCATTER_OCC;        // scatter CTAs per SM the launch bounds ask for
   static constexpr int TILE = THREADS * IPT;
   // local sort: capacity = the largest bucket that is finished on chip (everything larger gets another level)
   static constexpr int LOCAL_THREADS = sizeof(K) == 4 ? 384 : (VB == 0 ? 768 : 512);
-  static constexpr int LOCAL_IPT = sizeof(K) == 4 ? (VB == 8 ? 8 : 16) : (VB == 0 ? 12 : 8);
+  static constexpr int LOCAL_IPT = sizeof(K) == 4 ? (VB == 8 ? 8 : B200_LOCAL_IPT32) : (VB == 0 ? 12 : 8);
   static constexpr int LOCAL_CAP = LOCAL_THREADS * LOCAL_IPT;
   static constexpr uint32_t MERGE_CAP = LOCAL_CAP / 4;  // runs of tiny neighbouring buckets are merged up to this size
 };
@@ -55,9 +69,9 @@ inline cudaError_t persistent_grid(KernelT kernel, int threads, size_t smem, int
 template <typename K, int VB, int MODE, bool ORD>
 inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
-  auto kernel = scatter_kernel<K, VB, C::THREADS, C::IPT, MODE, ORD>;
+  auto kernel = scatter_kernel<K, VB, C::THREADS, C::IPT, C::OCC, MODE, ORD>;
   constexpr size_t smem = sizeof(ScatterSmem<K, VB, C::THREADS, C::IPT, MODE, ORD>);
-  static_assert(smem <= 113 * 1024, "two scatter CTAs must fit one SM's 228 KB of shared memory");
+  static_assert(smem <= 113 * 1024, "at least two scatter CTAs must fit one SM (228 KB of shared memory)");
   static int grid = 0;
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
