@@ -268,8 +268,10 @@ def run_ours_multi(args, rank, world):
         if pairs:
             vals.copy_(vsrc)
 
+    sorter = gd.DistSorter(n_l, torch.int32, torch.int32 if pairs else None, key_type=gs.KEY_U32, fused=not args.nccl_exchange)
+
     def step():
-        res["k"], res["v"], res["info"] = gd.distributed_sort(keys, vals, key_type=gs.KEY_U32, stable=pairs)
+        res["k"], res["v"], res["info"] = sorter.sort(keys, vals)
 
     clocks = ClockSampler(torch.cuda.current_device()); clocks.start()
     ms, wall = time_steps(step, restore, args.steps, args.warmup, dist.barrier)
@@ -298,7 +300,8 @@ def run_ours_multi(args, rank, world):
             "config": {"workload": f"{'cfg5-style pairs' if pairs else 'cfg2 weak-scaled'}: 2^{logn} uniform uint32 {'key+value pairs' if pairs else 'keys'} per GPU, one global array of {world}x2^{logn}, "
                                    "histogram all-reduce + key-range all-to-all over NVLink + local sort", "n_total": total, "n_per_gpu": n_l, "value_bytes": 4 if pairs else 0,
                        "l2": "inputs larger than L2; restored by an untimed D2D copy between steps", "timing": "CUDA events per step on each rank; max over ranks of the K-step sum"},
-            "exchange": {"imbalance": round(res["info"]["imbalance"], 4), "nvlink_bytes_out_per_gpu": int(n_l * kb * (world - 1) / world)},
+            "exchange": {"imbalance": round(res["info"]["imbalance"], 4), "nvlink_bytes_out_per_gpu": int(n_l * kb * (world - 1) / world),
+                         "fused_peer_scatter": bool(res["info"]["fused"])},
             "clocks": clk, "gpu_launches": None, "verified": bool(ok), "wall_s_timed_region": round(wall, 3)}
 
 
@@ -401,6 +404,7 @@ def main():
     ap.add_argument("--logn", type=int, default=0, help="override log2(keys per GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: NCCL all_to_all_single instead of the fused peer-memory scatter")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))

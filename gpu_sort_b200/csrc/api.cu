@@ -207,6 +207,19 @@ int b200_lsb_sort_host(const void* h_keys, const void* h_values, uint64_t num_it
   return sort_host(false, h_keys, h_values, num_items, h_sorted_keys, h_sorted_values, key_type, value_bytes, descending);
 }
 
+int b200_range_partition_to(void* d_temp, size_t* temp_bytes, const void* d_keys_in, const void* d_values_in, uint64_t num_items, int key_type,
+                            int value_bytes, int bits, const uint32_t* d_splitters, int num_parts, const uint64_t* d_local_counts,
+                            uint64_t* d_part_offsets, const uint64_t* d_dst_keys, const uint64_t* d_dst_values, const uint64_t* d_dst_base,
+                            b200_stream_t stream) {
+  Twiddle tw; int kb;
+  if (!make_twiddle(key_type, 0, &tw, &kb) || temp_bytes == nullptr) return (int)cudaErrorInvalidValue;
+  if (d_temp != nullptr && (d_dst_keys == nullptr || d_dst_base == nullptr || (value_bytes && d_dst_values == nullptr))) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_KV(kb, value_bytes, (range_partition_impl<K, V>(d_temp, temp_bytes, d_keys_in, d_values_in, nullptr, nullptr, num_items, tw, bits,
+                                                           d_splitters, num_parts, d_local_counts, d_part_offsets, d_dst_keys, d_dst_values,
+                                                           d_dst_base, s)));
+}
+
 int b200_range_partition(void* d_temp, size_t* temp_bytes, const void* d_keys_in, const void* d_values_in, void* d_keys_out,
                          void* d_values_out, uint64_t num_items, int key_type, int value_bytes, int bits,
                          const uint32_t* d_splitters, int num_parts, const uint64_t* d_local_counts, uint64_t* d_part_offsets,
@@ -216,7 +229,7 @@ int b200_range_partition(void* d_temp, size_t* temp_bytes, const void* d_keys_in
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   DISPATCH_KV(kb, value_bytes, (range_partition_impl<K, V>(d_temp, temp_bytes, d_keys_in, d_values_in, d_keys_out, d_values_out,
                                                            num_items, tw, bits, d_splitters, num_parts, d_local_counts,
-                                                           d_part_offsets, s)));
+                                                           d_part_offsets, nullptr, nullptr, nullptr, s)));
 }
 
 }  // extern "C"

@@ -95,6 +95,7 @@ struct TileHistArgs {
   uint32_t* tile_off; uint32_t* group_tail; uint32_t* group_flag;
   uint32_t* seg_hist;
   int shift; uint32_t mask; int tw_in; Twiddle tw;
+  const uint32_t* splitters; int num_parts;     // range mode: digit = #{ j < num_parts-1 : splitters[j] <= (key >> shift) }
 };
 
 template <typename K>
@@ -107,9 +108,21 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
   const int shift = a.shift; const uint32_t mask = a.mask;
   const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
   using S = typename std::make_signed<K>::type;
+  __shared__ uint32_t split[16];
+  const bool range = a.splitters != nullptr;
+  if (range && tid < 16) split[tid] = (int)tid < a.num_parts - 1 ? a.splitters[tid] : 0xFFFFFFFFu;
+  __syncthreads();
   auto count = [&](K k) {
     if (a.tw_in) k = (K)(k ^ (((K)((S)k >> (sizeof(K) * 8 - 1)) & fl) | sg) ^ fp);
-    atomicAdd(&sh[digit_of<K>(k, shift, mask)], 1u);
+    uint32_t d;
+    if (!range) d = digit_of<K>(k, shift, mask);
+    else {
+      const uint32_t b = (uint32_t)(k >> shift);
+      d = 0;
+#pragma unroll
+      for (int j = 0; j < 15; ++j) d += (j < a.num_parts - 1 && b >= split[j]) ? 1u : 0u;
+    }
+    atomicAdd(&sh[d], 1u);
   };
   for (uint32_t g = blockIdx.x; g < num_groups; g += gridDim.x) {
     const uint32_t t0 = g * HIST_GROUP, t1 = min(t0 + HIST_GROUP, num_tiles);

@@ -8,7 +8,8 @@
 //   MODE_LSB   : every pass of the stable LSB sort (one segment, onesweep style: digit starts from the up-front
 //                histogram, tile prefix by decoupled look-back, stable in-tile ranking).  Replaces
 //                DeviceRadixSortDownsweepKernel (lsb/cub/cub/device/dispatch/dispatch_radix_sort.cuh:164-196).
-//   MODE_RANGE : the multi-GPU send partition (stable; digit = destination rank by key range).
+//   MODE_RANGE : the multi-GPU send partition: MODE_SEG addressing (one segment, per-tile counts), stable, digit =
+//                destination rank by key range; every destination may live in its own buffer (peer GPU memory).
 //
 // The kernel is bound by instruction issue and shared-memory traffic long before HBM (DESIGN.md "Kernels"), so the
 // per-key path is kept minimal: full tiles take a path without any bounds checks, the order-preserving transform
@@ -38,19 +39,21 @@ struct ScatterArgs {
   const void* vals_in; void* vals_out;
   const TileDesc* descs;          // MODE_SEG: tile -> (offset, count, segment, tile in segment)
   const uint32_t* num_tiles_ptr;  // MODE_SEG: device-side tile count
-  uint32_t num_tiles;             // MODE_LSB / MODE_RANGE
-  uint64_t base, n;               // MODE_LSB / MODE_RANGE: the launch covers keys [base, base+n)
+  uint32_t num_tiles;             // MODE_LSB
+  uint64_t base, n;               // MODE_LSB: the launch covers keys [base, base+n)
   const uint64_t* bins;           // MODE_SEG: [segment][256] absolute output index of the start of each sub-bucket;
                                   // otherwise [256] absolute output index of the start of each digit
   const uint32_t* tile_off;       // MODE_SEG: [tile][256]  keys of the same (segment, digit) in earlier tiles of the tile's group
   const uint32_t* carry;          // MODE_SEG: [group][256] ... and in earlier groups (tile_hist_kernel / group_carry_kernel)
-  uint64_t* bins_next;            // MODE_LSB / MODE_RANGE: the last tile writes bins + portion counts here (or nullptr)
-  uint32_t* status;               // MODE_LSB / MODE_RANGE: [tile][256] look-back words, zeroed before the launch
-  uint32_t* ticket;               // MODE_LSB / MODE_RANGE: zeroed before the launch
+  uint64_t* bins_next;            // MODE_LSB: the last tile writes bins + portion counts here (or nullptr)
+  uint32_t* status;               // MODE_LSB: [tile][256] look-back words, zeroed before the launch
+  uint32_t* ticket;               // MODE_LSB: zeroed before the launch
   int shift; uint32_t mask;
   int tw_in, tw_out;
   Twiddle tw;
   const uint32_t* splitters; int num_parts;     // MODE_RANGE: digit = #{ j < num_parts-1 : splitters[j] <= (key >> shift) }
+  const uint64_t* dst_keys; const uint64_t* dst_vals;   // MODE_RANGE: [num_parts] base ADDRESS of every destination's key / value buffer
+                                                        // (nullptr: keys_out / vals_out for all); bins[d] = first index inside that buffer
 };
 
 constexpr int MAX_PARTS = 16;
@@ -64,7 +67,7 @@ template <typename K, int VB, int THREADS, int IPT, int MODE, bool ORD>
 struct ScatterSmem {
   static constexpr int TILE = THREADS * IPT;
   static constexpr int WARPS = THREADS / 32;
-  static constexpr bool ORDERED = MODE != MODE_SEG || ORD;
+  static constexpr bool ORDERED = MODE == MODE_LSB || ORD;
   using V = typename ValType<VB>::type;
   static constexpr int SLACK = 16 / sizeof(K), VSLACK = 16 / sizeof(V);
   alignas(16) K stage[2][TILE + SLACK];
@@ -255,7 +258,7 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
   uint32_t* stw = nullptr;
   const bool first = g.tile_in_seg == 0;
   if (tid < RADIX) {
-    if (MODE == MODE_SEG) {
+    if (MODE != MODE_LSB) {
       // destination = start of the (segment, digit) sub-bucket + keys of it in earlier tiles: three independent loads whose
       // latency hides behind the scan and the shared-memory reorder below
       const uint32_t grp = g.tile / HIST_GROUP;
@@ -321,13 +324,19 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
 
   // ---- digit owners: global start of this tile's run of every digit -> destination pointers
   if (tid < RADIX) {
-    if (MODE != MODE_SEG) {
+    if (MODE == MODE_LSB) {
       if (LB_POS == 0) excl_g = first ? 0u : lookback(a.status + tid, g.tile, g.tile_in_seg, stw, my_total);
       gstart = a.bins[tid] + excl_g;
       if (a.bins_next != nullptr && g.tile == num_tiles - 1) a.bins_next[tid] = gstart + my_total;
     }
-    sm.kptr[tid] = reinterpret_cast<K*>(a.keys_out) + (gstart - my_excl);
-    if (VB) sm.vptr[tid] = reinterpret_cast<V*>(a.vals_out) + (gstart - my_excl);
+    K* kbase = reinterpret_cast<K*>(a.keys_out);
+    V* vbase = reinterpret_cast<V*>(a.vals_out);
+    if (MODE == MODE_RANGE && a.dst_keys != nullptr && (int)tid < a.num_parts) {       // per-destination buffers (peer memory)
+      kbase = reinterpret_cast<K*>(a.dst_keys[tid]);
+      if (VB) vbase = reinterpret_cast<V*>(a.dst_vals[tid]);
+    }
+    sm.kptr[tid] = kbase + (gstart - my_excl);
+    if (VB) sm.vptr[tid] = vbase + (gstart - my_excl);
   }
   __syncthreads();        // keys are in place, every thread has read its values, kptr/vptr are published
   if (VB) {
@@ -385,14 +394,14 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_kernel(const __grid_cons
   const unsigned tid = threadIdx.x;
   const K* __restrict__ keys_in = reinterpret_cast<const K*>(a.keys_in);
   const V* __restrict__ vals_in = reinterpret_cast<const V*>(a.vals_in);
-  const uint32_t num_tiles = MODE == MODE_SEG ? *a.num_tiles_ptr : a.num_tiles;
+  const uint32_t num_tiles = MODE != MODE_LSB ? *a.num_tiles_ptr : a.num_tiles;
 
   // producer: describe tile `t`, arm the slot's barrier and launch the bulk copies of its keys (and values)
   auto stage_tile = [&](int slot, uint32_t t, const TileDesc& td) {
     TileGeom g;
     g.tile = t; g.skew = 0; g.vskew = 0;
     if (t < num_tiles) {
-      if (MODE == MODE_SEG) { g.off = td.off; g.cnt = td.cnt; g.seg = td.seg; g.tile_in_seg = td.tile_in_seg; }
+      if (MODE != MODE_LSB) { g.off = td.off; g.cnt = td.cnt; g.seg = td.seg; g.tile_in_seg = td.tile_in_seg; }
       else {
         const uint64_t rel = (uint64_t)t * TILE;
         g.off = a.base + rel; g.cnt = (uint32_t)(a.n - rel < (uint64_t)TILE ? a.n - rel : (uint64_t)TILE);
@@ -428,11 +437,11 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_kernel(const __grid_cons
   if (tid == PRODUCER) {
     mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1);
     mbar_fence_init();
-    const uint32_t t0 = MODE != MODE_SEG ? atomicAdd(a.ticket, 1u) : blockIdx.x;
-    tk_a = MODE != MODE_SEG ? atomicAdd(a.ticket, 1u) : t0 + gridDim.x;
+    const uint32_t t0 = MODE == MODE_LSB ? atomicAdd(a.ticket, 1u) : blockIdx.x;
+    tk_a = MODE == MODE_LSB ? atomicAdd(a.ticket, 1u) : t0 + gridDim.x;
     TileDesc td{};
-    if (MODE == MODE_SEG && t0 < num_tiles) td = a.descs[t0];
-    if (MODE == MODE_SEG && tk_a < num_tiles) td_a = a.descs[tk_a];
+    if (MODE != MODE_LSB && t0 < num_tiles) td = a.descs[t0];
+    if (MODE != MODE_LSB && tk_a < num_tiles) td_a = a.descs[tk_a];
     stage_tile(0, t0, td);
   }
   if (tid == 0) sm.skewed = 0;
@@ -445,8 +454,8 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_kernel(const __grid_cons
     if (g.tile >= num_tiles) break;
     if (tid == PRODUCER) {
       stage_tile(slot ^ 1, tk_a, td_a);          // the other slot is free: its tile finished last iteration
-      tk_b = MODE != MODE_SEG ? atomicAdd(a.ticket, 1u) : tk_a + gridDim.x;
-      if (MODE == MODE_SEG && tk_b < num_tiles) td_b = a.descs[tk_b];
+      tk_b = MODE == MODE_LSB ? atomicAdd(a.ticket, 1u) : tk_a + gridDim.x;
+      if (MODE != MODE_LSB && tk_b < num_tiles) td_b = a.descs[tk_b];
     }
     if (g.cnt == (uint32_t)TILE) scatter_tile<K, VB, THREADS, IPT, MODE, ORD, true>(a, sm, g, slot, num_tiles, it);
     else scatter_tile<K, VB, THREADS, IPT, MODE, ORD, false>(a, sm, g, slot, num_tiles, it);

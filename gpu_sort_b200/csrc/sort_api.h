@@ -30,6 +30,7 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
 template <typename K, int VB>
 cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* kin, const void* vin, void* kout, void* vout,
                                  uint64_t n, const Twiddle& tw, int bits, const uint32_t* d_splitters, int num_parts,
-                                 const uint64_t* d_local_counts, uint64_t* d_part_offsets, cudaStream_t s);
+                                 const uint64_t* d_local_counts, uint64_t* d_part_offsets, const uint64_t* d_dst_keys, const uint64_t* d_dst_vals,
+                                 const uint64_t* d_dst_base, cudaStream_t s);
 
 }  // namespace b200

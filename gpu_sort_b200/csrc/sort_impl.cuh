@@ -387,7 +387,7 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
 // rank's own top-`bits` histogram (b200_msd_histogram), from which the part sizes follow without another read.
 // ===============================================================================================================
 static __global__ void __launch_bounds__(256) part_offsets_kernel(const uint64_t* counts, int nbuckets, const uint32_t* splitters, int num_parts,
-                                                                 uint64_t* part_offsets, uint64_t* bins) {
+                                                                 uint64_t* part_offsets, uint64_t* bins, const uint64_t* dst_base) {
   __shared__ unsigned long long sums[MAX_PARTS];
   __shared__ uint32_t sp[MAX_PARTS];
   if (threadIdx.x < MAX_PARTS) { sums[threadIdx.x] = 0; sp[threadIdx.x] = (int)threadIdx.x < num_parts - 1 ? splitters[threadIdx.x] : 0xFFFFFFFFu; }
@@ -404,7 +404,7 @@ static __global__ void __launch_bounds__(256) part_offsets_kernel(const uint64_t
   if (threadIdx.x == 0) {
     uint64_t run = 0;
     for (int d = 0; d < RADIX; ++d) {
-      bins[d] = run;
+      bins[d] = (dst_base != nullptr) ? (d < num_parts ? dst_base[d] : 0ull) : run;       // own buffer per destination: caller's base
       if (d <= num_parts) part_offsets[d] = run;
       if (d < num_parts) run += sums[d];
     }
@@ -414,35 +414,50 @@ static __global__ void __launch_bounds__(256) part_offsets_kernel(const uint64_t
 template <typename K, int VB>
 cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* kin, const void* vin, void* kout, void* vout,
                                  uint64_t n, const Twiddle& tw, int bits, const uint32_t* d_splitters, int num_parts,
-                                 const uint64_t* d_local_counts, uint64_t* d_part_offsets, cudaStream_t s) {
+                                 const uint64_t* d_local_counts, uint64_t* d_part_offsets, const uint64_t* d_dst_keys, const uint64_t* d_dst_vals,
+                                 const uint64_t* d_dst_base, cudaStream_t s) {
   using C = Cfg<K, VB>;
   constexpr int KEY_BITS = sizeof(K) * 8;
-  if (num_parts < 1 || num_parts > MAX_PARTS || bits < 1 || bits > 16) return cudaErrorInvalidValue;
-  const uint64_t portion = (MAX_PORTION / C::TILE) * C::TILE;
-  const uint64_t max_tiles = (std::min<uint64_t>(n, portion) + C::TILE - 1) / C::TILE;
+  if (num_parts < 1 || num_parts > MAX_PARTS || bits < 1 || bits > 16 || n >= (1ull << 32)) return cudaErrorInvalidValue;
+  const uint32_t max_tiles = (uint32_t)(n / C::TILE) + 2;
+  const uint32_t max_groups = max_tiles / HIST_GROUP + 1;
   Carver cv(d_temp);
   uint64_t* bins = cv.take<uint64_t>(RADIX);
-  uint64_t* pbins = cv.take<uint64_t>(2 * RADIX);
-  uint32_t* tick_status = cv.take<uint32_t>(64 + max_tiles * RADIX);
+  MsbCounters* ctr = cv.take<MsbCounters>(1);
+  Seg* seg = cv.take<Seg>(2);
+  uint32_t* tile_base = cv.take<uint32_t>(4);
+  TileDesc* descs = cv.take<TileDesc>(max_tiles);
+  uint32_t* seg_hist = cv.take<uint32_t>(RADIX);
+  uint32_t* tile_off = cv.take<uint32_t>((size_t)max_tiles * RADIX);
+  uint32_t* group_tail = cv.take<uint32_t>((size_t)max_groups * RADIX);
+  uint32_t* group_flag = cv.take<uint32_t>(max_groups);
+  uint32_t* carry = cv.take<uint32_t>((size_t)max_groups * RADIX);
   if (d_temp == nullptr) { *temp_bytes = std::max<size_t>(cv.total(), 256); return cudaSuccess; }
   if (*temp_bytes < cv.total()) return cudaErrorInvalidValue;
-  part_offsets_kernel<<<1, 256, 0, s>>>(d_local_counts, 1 << bits, d_splitters, num_parts, d_part_offsets, bins);
-  int q = 0;
-  for (uint64_t base = 0; base < n; base += portion, ++q) {
-    const uint64_t pn = std::min<uint64_t>(portion, n - base);
-    const uint32_t tiles = (uint32_t)((pn + C::TILE - 1) / C::TILE);
-    B200_CHECK(cudaMemsetAsync(tick_status, 0, (64 + (size_t)tiles * RADIX) * sizeof(uint32_t), s));
-    ScatterArgs pa{};
-    pa.keys_in = kin; pa.keys_out = kout; pa.vals_in = vin; pa.vals_out = vout;
-    pa.num_tiles = tiles; pa.base = base; pa.n = pn;
-    pa.bins = (q == 0) ? bins : pbins + ((q - 1) & 1) * RADIX;
-    pa.bins_next = (base + pn < n) ? pbins + (q & 1) * RADIX : nullptr;
-    pa.status = tick_status + 64; pa.ticket = tick_status;
-    pa.shift = KEY_BITS - bits; pa.mask = (uint32_t)(num_parts - 1);
-    pa.tw_in = 1; pa.tw_out = 1; pa.tw = tw;
-    pa.splitters = d_splitters; pa.num_parts = num_parts;
-    B200_CHECK((launch_scatter<K, VB, MODE_RANGE, true>(pa, tiles, s)));
-  }
+  // part sizes follow from the caller's own top-bits histogram; bins[d] = start of part d (in the shared output, or 0-based
+  // inside its own destination buffer + the caller's base when every part has its own buffer)
+  part_offsets_kernel<<<1, 256, 0, s>>>(d_local_counts, 1 << bits, d_splitters, num_parts, d_part_offsets, bins, d_dst_keys ? d_dst_base : nullptr);
+  if (n == 0) return cudaGetLastError();
+  const int sms = num_sms();
+  B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
+  B200_CHECK(cudaMemsetAsync(seg_hist, 0, RADIX * sizeof(uint32_t), s));
+  msb_init_kernel<<<1, 32, 0, s>>>(seg, ctr, n);
+  scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(seg, &ctr->num_segs[0], tile_base, &ctr->num_tiles[0], max_tiles, &ctr->error, C::TILE);
+  fill_descs_kernel<<<sms * 2, 256, 0, s>>>(seg, tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], descs, C::TILE);
+  TileHistArgs ha{};
+  ha.keys = kin; ha.descs = descs; ha.num_tiles_ptr = &ctr->num_tiles[0];
+  ha.tile_off = tile_off; ha.group_tail = group_tail; ha.group_flag = group_flag; ha.seg_hist = seg_hist;
+  ha.shift = KEY_BITS - bits; ha.mask = 0xFFu; ha.tw_in = 1; ha.tw = tw; ha.splitters = d_splitters; ha.num_parts = num_parts;
+  { ProfScope prof("tile_hist", s); tile_hist_kernel<K><<<(int)std::min<uint32_t>(max_groups, (uint32_t)sms * 4), HIST_THREADS, 0, s>>>(ha); }
+  group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(group_tail, group_flag, carry, &ctr->num_tiles[0]);
+  ScatterArgs pa{};
+  pa.keys_in = kin; pa.keys_out = kout; pa.vals_in = vin; pa.vals_out = vout;
+  pa.descs = descs; pa.num_tiles_ptr = &ctr->num_tiles[0];
+  pa.bins = bins; pa.tile_off = tile_off; pa.carry = carry;
+  pa.shift = KEY_BITS - bits; pa.mask = (uint32_t)(num_parts - 1);
+  pa.tw_in = 1; pa.tw_out = 1; pa.tw = tw;
+  pa.splitters = d_splitters; pa.num_parts = num_parts; pa.dst_keys = d_dst_keys; pa.dst_vals = d_dst_vals;
+  B200_CHECK((launch_scatter<K, VB, MODE_RANGE, true>(pa, max_tiles, s)));
   return cudaGetLastError();
 }
 

@@ -102,9 +102,24 @@ __global__ void __launch_bounds__(512) msd_hist_kernel(const K* keys, uint64_t n
   for (int i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const int shift = (int)sizeof(K) * 8 - bits;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    atomicAdd(&sh[(uint32_t)(twiddle_in<K>(keys[i], tw) >> shift)], 1u);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto count = [&](K k) { atomicAdd(&sh[(uint32_t)(twiddle_in<K>(k, tw) >> shift)], 1u); };
+  // 16-byte vector loads, four in flight per thread, when the pointer allows it; scalar tail
+  constexpr uint64_t VEC = 16 / sizeof(K);
+  const uint64_t nvec = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0 ? n / VEC : 0;
+  const uint4* pv = reinterpret_cast<const uint4*>(keys);
+  for (uint64_t i0 = t0; i0 < nvec; i0 += 4 * stride) {
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = i0 + u * stride < nvec ? pv[i0 + u * stride] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * stride < nvec) {
+        if (sizeof(K) == 4) { count((K)q[u].x); count((K)q[u].y); count((K)q[u].z); count((K)q[u].w); }
+        else { count((K)(((uint64_t)q[u].y << 32) | q[u].x)); count((K)(((uint64_t)q[u].w << 32) | q[u].z)); }
+      }
+  }
+  for (uint64_t i = nvec * VEC + t0; i < n; i += stride) count(keys[i]);
   __syncthreads();
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
     const uint32_t c = sh[i];
@@ -181,7 +196,7 @@ int b200_msd_histogram(const void* d_keys, uint64_t num_items, int key_type, int
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int g = sms * 2;
+  const int g = sms * 4;
   if (kb == 4) {
     if ((e = cudaFuncSetAttribute(msd_hist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536)) != cudaSuccess) return (int)e;
     msd_hist_kernel<uint32_t><<<g, 512, smem, s>>>(reinterpret_cast<const uint32_t*>(d_keys), num_items, tw, bits, reinterpret_cast<unsigned long long*>(d_counts));

@@ -117,6 +117,30 @@ def choose_splitters(global_counts, parts: int) -> List[int]:
     return out
 
 
+def choose_splitters_tensor(global_counts: torch.Tensor, parts: int) -> torch.Tensor:
+    """choose_splitters with torch ops on the tensor's own device (no device->host copy of the histogram); int32[parts-1].
+    Same rule, same tie-break: tests/test_dist_cpu.py checks it against the host version."""
+    c = global_counts.to(torch.float64)
+    cum = torch.cat([torch.zeros(1, dtype=torch.float64, device=c.device), torch.cumsum(c, 0)])
+    n = cum[-1]
+    targets = n * torch.arange(1, parts, dtype=torch.float64, device=c.device) / parts
+    b = torch.searchsorted(cum, targets, right=False).clamp_(0, c.numel())
+    lower = (b - 1).clamp_(min=0)
+    take_lower = (b > 0) & ((cum[lower] - targets).abs() <= (cum[b] - targets).abs())
+    b = torch.where(take_lower, lower, b)
+    b = torch.cummax(b, 0).values if parts > 1 else b
+    return b.to(torch.int32)
+
+
+def part_counts(local_counts: torch.Tensor, splitters: torch.Tensor, parts: int) -> torch.Tensor:
+    """Keys this rank sends to every destination: sum of its own bucket counts inside each splitter range; int64[parts]."""
+    bucket = torch.arange(local_counts.numel(), device=local_counts.device, dtype=torch.int32)
+    dest = torch.searchsorted(splitters.to(torch.int32), bucket, right=True) if parts > 1 else torch.zeros_like(bucket, dtype=torch.int64)
+    out = torch.zeros(parts, dtype=torch.int64, device=local_counts.device)
+    out.scatter_add_(0, dest.to(torch.int64), local_counts.to(torch.int64))
+    return out
+
+
 def receive_layout(count_matrix: np.ndarray, rank: int) -> Tuple[List[int], List[int], int]:
     """count_matrix[src][dst] = keys src sends to dst.  Returns (send_sizes, recv_sizes, n_recv) for `rank`; the receive
     buffer is filled in source-rank order, which is what keeps the distributed sort stable."""
@@ -173,3 +197,127 @@ def distributed_sort(keys: torch.Tensor, vals: Optional[torch.Tensor] = None, gr
     sk, sv = ops.local_sort(rk, rv, n_recv, stable) if n_recv else (rk, rv)   # 7
     info = {"count": n_recv, "count_matrix": matrix, "splitters": splitters, "imbalance": imbalance(matrix)}
     return sk, sv, info
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The CUDA fast path: buffers allocated once, exchange fused into the scatter kernel over NVLink peer memory
+# ----------------------------------------------------------------------------------------------------------------
+class DistSorter:
+    """Multi-GPU sort with everything allocated up front (one process per GPU).
+
+    fused=True (default): the receive buffers live in symmetric memory (torch.distributed._symmetric_memory: every rank maps
+    every peer's buffer); the range-partition kernel writes each destination's part STRAIGHT into that GPU's receive buffer
+    (b200_range_partition_to: coalesced 128-byte runs over NVLink from inside the scatter's write-out), so the key/value
+    all-to-all is not a separate collective and overlaps the partition tile by tile.  The only collectives left are the
+    512 KB histogram all-reduce, the GxG count all-gather and two barriers.
+    fused=False: the NCCL baseline (partition into a local send buffer, then all_to_all_single).
+    """
+
+    def __init__(self, n_local: int, key_dtype=torch.int32, value_dtype=None, group=None, bits: int = DEFAULT_BITS, slack: float = 1.15,
+                 fused: bool = True, key_type: Optional[int] = None, stable: Optional[bool] = None):
+        import gpu_sort_b200 as gs
+        self.gs, self.group, self.bits = gs, group, bits
+        self.G, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.kt = key_type if key_type is not None else gs._TORCH_KEY[key_dtype]
+        self.pairs = value_dtype is not None
+        self.stable = self.pairs if stable is None else stable
+        self.n_local = n_local
+        self.cap = int(n_local * slack) + 4096
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.fused = fused and self.G > 1
+        self.hk = self.hv = None
+        if self.fused:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                gname = (group or dist.group.WORLD).group_name
+                self.recv_k = symm.empty(self.cap, dtype=key_dtype, device=dev)
+                self.hk = symm.rendezvous(self.recv_k, gname)
+                ptrs_k = [int(p) for p in self.hk.buffer_ptrs]
+                ptrs_v = [0] * self.G
+                if self.pairs:
+                    self.recv_v = symm.empty(self.cap, dtype=value_dtype, device=dev)
+                    self.hv = symm.rendezvous(self.recv_v, gname)
+                    ptrs_v = [int(p) for p in self.hv.buffer_ptrs]
+                self.dst_k = torch.tensor(ptrs_k, dtype=torch.int64, device=dev)
+                self.dst_v = torch.tensor(ptrs_v, dtype=torch.int64, device=dev)
+            except Exception as e:       # no peer mapping on this system: NCCL exchange (still the CUDA path, nothing on the CPU)
+                self.fused = False
+                self.fused_error = repr(e)
+        if not self.fused:
+            self.recv_k = torch.empty(self.cap, dtype=key_dtype, device=dev)
+            self.recv_v = torch.empty(self.cap, dtype=value_dtype, device=dev) if self.pairs else None
+            self.send_k = torch.empty(n_local, dtype=key_dtype, device=dev)
+            self.send_v = torch.empty(n_local, dtype=value_dtype, device=dev) if self.pairs else None
+        elif not self.pairs:
+            self.recv_v = None
+        self.alt_k = torch.empty(self.cap, dtype=key_dtype, device=dev)
+        self.alt_v = torch.empty(self.cap, dtype=value_dtype, device=dev) if self.pairs else None
+        self.counts = torch.empty(1 << bits, dtype=torch.int64, device=dev)
+        self.offs = torch.zeros(self.G + 1, dtype=torch.int64, device=dev)
+        vb = gs._value_bytes(self.recv_v)
+        self.vb = vb
+        nb = ctypes.c_size_t(0)
+        gs._check(gs.lib.b200_range_partition(None, ctypes.byref(nb), None, None, None, None, n_local, self.kt, vb, bits, None, self.G, None, None, None),
+                  "b200_range_partition(size query)")
+        self.part_temp = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        if self.stable:
+            tb = ctypes.c_size_t(0)
+            gs._check(gs.lib.b200_lsb_sort(None, ctypes.byref(tb), None, None, None, None, None, self.cap, self.kt, vb, 0, gs.KEY_BYTES[self.kt] * 8, 0, 1, None),
+                      "b200_lsb_sort(size query)")
+            self.sort_temp = torch.empty(tb.value, dtype=torch.uint8, device=dev)
+        else:
+            self.sort_temp = torch.empty(gs.rdxsrt_workspace_bytes(self.cap, self.kt, vb), dtype=torch.uint8, device=dev)
+
+    def sort(self, keys: torch.Tensor, vals: Optional[torch.Tensor] = None):
+        gs, G, rank, bits = self.gs, self.G, self.rank, self.bits
+        n = keys.numel()
+        stream = gs._stream(None)
+        gs._check(gs.lib.b200_msd_histogram(gs._ptr(keys), n, self.kt, bits, gs._ptr(self.counts), stream), "b200_msd_histogram")       # 1
+        glob = self.counts
+        if G > 1:
+            glob = self.counts.clone()
+            dist.all_reduce(glob, group=self.group)                                                                                   # 2
+        sp = choose_splitters_tensor(glob, G)                                                                                         # 3 (device)
+        spp = torch.cat([sp, sp.new_zeros(1)])
+        mine = part_counts(self.counts, sp, G)                                                                                        # 5
+        if G > 1:
+            mat = torch.empty(G * G, dtype=torch.int64, device=keys.device)
+            dist.all_gather_into_tensor(mat, mine, group=self.group)
+            mat = mat.view(G, G)
+        else:
+            mat = mine.view(1, 1)
+        base = mat[:rank].sum(0) if rank > 0 else torch.zeros(G, dtype=torch.int64, device=keys.device)      # my start inside every destination
+        matrix = mat.cpu().numpy()                                   # the one host sync: n_recv sizes the local sort
+        send, recv, n_recv = receive_layout(matrix, rank)
+        if n_recv > self.cap:
+            raise RuntimeError(f"rank {rank}: {n_recv} keys to receive exceed the receive capacity {self.cap} (key range too skewed for range partitioning)")
+        nb = ctypes.c_size_t(self.part_temp.numel())
+        if self.fused:
+            self.hk.barrier()                                        # every peer is done with the previous contents of its receive buffer
+            gs._check(gs.lib.b200_range_partition_to(gs._ptr(self.part_temp), ctypes.byref(nb), gs._ptr(keys), gs._ptr(vals), n, self.kt, self.vb, bits,
+                                                     gs._ptr(spp), G, gs._ptr(self.counts), gs._ptr(self.offs), gs._ptr(self.dst_k), gs._ptr(self.dst_v),
+                                                     gs._ptr(base.contiguous()), stream), "b200_range_partition_to")                  # 4 + 6 fused
+            self.hk.barrier()                                        # all peers' stores have landed
+        else:
+            gs._check(gs.lib.b200_range_partition(gs._ptr(self.part_temp), ctypes.byref(nb), gs._ptr(keys), gs._ptr(vals), gs._ptr(self.send_k),
+                                                  gs._ptr(self.send_v), n, self.kt, self.vb, bits, gs._ptr(spp), G, gs._ptr(self.counts), gs._ptr(self.offs),
+                                                  stream), "b200_range_partition")                                                    # 4
+            if G > 1:
+                dist.all_to_all_single(self.recv_k[:n_recv], self.send_k, output_split_sizes=recv, input_split_sizes=send, group=self.group)   # 6
+                if self.pairs:
+                    dist.all_to_all_single(self.recv_v[:n_recv], self.send_v, output_split_sizes=recv, input_split_sizes=send, group=self.group)
+            else:
+                self.recv_k[:n].copy_(self.send_k)
+                if self.pairs:
+                    self.recv_v[:n].copy_(self.send_v)
+        rk = self.recv_k[:n_recv]; rv = self.recv_v[:n_recv] if self.pairs else None
+        if n_recv == 0:
+            sk, sv = rk, rv
+        elif self.stable:                                                                                                             # 7
+            dk = gs.DoubleBuffer(rk, self.alt_k[:n_recv]); dv = gs.DoubleBuffer(rv, self.alt_v[:n_recv]) if self.pairs else None
+            gs.DeviceRadixSort._run(self.sort_temp, dk, dv, n_recv, 0, None, False, None, self.kt)
+            sk, sv = dk.Current(), (dv.Current() if self.pairs else None)
+        else:
+            r = gs.rdxsrt_unstable_sort(rk, rv, n_recv, self.alt_k[:n_recv], self.alt_v[:n_recv] if self.pairs else None, workspace=self.sort_temp, key_type=self.kt)
+            sk, sv = r.sorted_keys, r.sorted_values
+        return sk, sv, {"count": n_recv, "count_matrix": matrix, "imbalance": imbalance(matrix), "fused": self.fused}

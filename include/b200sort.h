@@ -124,6 +124,19 @@ B200_API int b200_range_partition(void* d_temp, size_t* temp_bytes,
                          uint64_t num_items, int key_type, int value_bytes, int bits,
                          const uint32_t* d_splitters, int num_parts, const uint64_t* d_local_counts,
                          uint64_t* d_part_offsets, b200_stream_t stream);
+/* The same partition FUSED with the exchange: part j is written straight into its own destination buffer -- normally
+ * the receive buffer of GPU j, mapped into this process (peer memory over NVLink) -- so the all-to-all happens inside the
+ * scatter kernel's coalesced write-out, tile by tile, instead of as a separate collective.
+ *   d_dst_keys / d_dst_values : uint64[num_parts] on the device, base ADDRESS of destination j's key / value buffer
+ *   d_dst_base                : uint64[num_parts] on the device, index inside destination j's buffer where this rank's part
+ *                               begins (sum of the counts of lower source ranks, from the all-gathered count matrix)
+ * The caller synchronises the ranks after the kernel (all peers' stores must have landed before the local sort). */
+B200_API int b200_range_partition_to(void* d_temp, size_t* temp_bytes,
+                            const void* d_keys_in, const void* d_values_in,
+                            uint64_t num_items, int key_type, int value_bytes, int bits,
+                            const uint32_t* d_splitters, int num_parts, const uint64_t* d_local_counts,
+                            uint64_t* d_part_offsets, const uint64_t* d_dst_keys, const uint64_t* d_dst_values,
+                            const uint64_t* d_dst_base, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Benchmark / test utilities that run on the device (synthetic inputs of SURVEY.md section 8d and size-independent

@@ -78,9 +78,10 @@ def test_product_never_references_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in text and "oracle_lib" not in text and "oracle/" not in text.replace("oracle/radix_oracle.c", ""), f
-    for f in os.listdir(os.path.join(ROOT, "include")):
-        text = open(os.path.join(ROOT, "include", f)).read()
-        assert "liboracle" not in text
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
+        for f in files:
+            text = open(os.path.join(dirpath, f)).read()
+            assert "liboracle" not in text
 
 
 def test_python_host_layer_fails_loudly_without_the_library(tmp_path):

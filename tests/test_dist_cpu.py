@@ -105,6 +105,11 @@ def test_choose_splitters_properties():
         for j, b in enumerate(s, 1):       # no other boundary is closer to the ideal split point
             target = cum[-1] * j / parts
             assert abs(cum[b] - target) <= np.abs(cum - target).min() + 1e-9
+        assert gd.choose_splitters_tensor(torch.from_numpy(c.astype(np.int64)), parts).tolist() == s
+        if parts > 1:
+            pc = gd.part_counts(torch.from_numpy(c.astype(np.int64)), torch.tensor(s, dtype=torch.int32), parts)
+            edges = [0] + s + [4096]
+            assert pc.tolist() == [int(c[edges[i]:edges[i + 1]].sum()) for i in range(parts)]
     # one bucket holds everything (constant keys): all splitters collapse around it, nothing is lost
     c = np.zeros(256, dtype=np.uint64); c[77] = 10**6
     s = gd.choose_splitters(c, 4)
