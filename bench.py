@@ -276,6 +276,7 @@ def run_ours_multi(args, rank, world):
     clocks = ClockSampler(torch.cuda.current_device()); clocks.start()
     ms, wall = time_steps(step, restore, args.steps, args.warmup, dist.barrier)
     clk = clocks.stop()
+    restore(); pinfo = sorter.sort(keys, vals, profile=True)[2]; phases = dict(pinfo.get("phases_ms", {}), kernels=pinfo.get("kernels_ms"))
     t = torch.tensor([float(np.sum(ms))], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)                       # max over ranks of the device-timed K steps
     total_ms = float(t.item())
@@ -301,7 +302,7 @@ def run_ours_multi(args, rank, world):
                                    "histogram all-reduce + key-range all-to-all over NVLink + local sort", "n_total": total, "n_per_gpu": n_l, "value_bytes": 4 if pairs else 0,
                        "l2": "inputs larger than L2; restored by an untimed D2D copy between steps", "timing": "CUDA events per step on each rank; max over ranks of the K-step sum"},
             "exchange": {"imbalance": round(res["info"]["imbalance"], 4), "nvlink_bytes_out_per_gpu": int(n_l * kb * (world - 1) / world),
-                         "fused_peer_scatter": bool(res["info"]["fused"])},
+                         "fused_peer_scatter": bool(res["info"]["fused"]), "phases_ms_rank0": phases},
             "clocks": clk, "gpu_launches": None, "verified": bool(ok), "wall_s_timed_region": round(wall, 3)}
 
 

@@ -56,6 +56,10 @@ def _load():
     lib.b200_lsb_sort.argtypes = [vp, P(sz), vp, vp, vp, vp, P(i32), u64, i32, i32, i32, i32, i32, i32, vp]
     lib.b200_msb_sort.restype = i32
     lib.b200_msb_sort.argtypes = [vp, vp, u64, vp, vp, i32, i32, vp, P(sz), vp, P(vp), P(vp)]
+    lib.b200_msb_sort_bits.restype = i32
+    lib.b200_msb_sort_bits.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, i32, vp, P(sz), vp, P(vp), P(vp)]
+    lib.b200_range_partition_to.restype = i32
+    lib.b200_range_partition_to.argtypes = [vp, P(sz), vp, vp, u64, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.b200_msb_sort_host.restype = i32
     lib.b200_msb_sort_host.argtypes = [vp, vp, u64, vp, vp, i32, i32]
     lib.b200_lsb_sort_host.restype = i32
@@ -213,18 +217,20 @@ def rdxsrt_workspace_bytes(num_items: int, key_type: int, value_bytes: int) -> i
 
 def rdxsrt_unstable_sort(dev_keys: torch.Tensor, dev_values: Optional[torch.Tensor], key_count: int,
                          dev_sorted_keys_out: torch.Tensor, dev_sorted_values_out: Optional[torch.Tensor],
-                         workspace: Optional[torch.Tensor] = None, stream=None, key_type: Optional[int] = None) -> RDXSRT_SortedSequence:
-    """rdxsrt_unstable_sort<KeyT,ValueT,IndexT> (msb/src/sort/gpu_radix_sort.h:187-507).  Both buffer pairs are clobbered."""
+                         workspace: Optional[torch.Tensor] = None, stream=None, key_type: Optional[int] = None,
+                         begin_bit: int = 0, end_bit: int = 64) -> RDXSRT_SortedSequence:
+    """rdxsrt_unstable_sort<KeyT,ValueT,IndexT> (msb/src/sort/gpu_radix_sort.h:187-507).  Both buffer pairs are clobbered.
+    begin_bit / end_bit (b200_msb_sort_bits) restrict the comparison to those bits of the transformed key."""
     kt = key_type_of(dev_keys, key_type)
     vb = _value_bytes(dev_values)
     ok, ov = ctypes.c_void_p(0), ctypes.c_void_p(0)
     if workspace is None:
-        err = lib.b200_msb_sort(_ptr(dev_keys), _ptr(dev_values), key_count, _ptr(dev_sorted_keys_out), _ptr(dev_sorted_values_out),
-                                kt, vb, None, None, _stream(stream), ctypes.byref(ok), ctypes.byref(ov))
+        err = lib.b200_msb_sort_bits(_ptr(dev_keys), _ptr(dev_values), key_count, _ptr(dev_sorted_keys_out), _ptr(dev_sorted_values_out),
+                                     kt, vb, begin_bit, end_bit, None, None, _stream(stream), ctypes.byref(ok), ctypes.byref(ov))
     else:
         nbytes = ctypes.c_size_t(workspace.numel() * workspace.element_size())
-        err = lib.b200_msb_sort(_ptr(dev_keys), _ptr(dev_values), key_count, _ptr(dev_sorted_keys_out), _ptr(dev_sorted_values_out),
-                                kt, vb, _ptr(workspace), ctypes.byref(nbytes), _stream(stream), ctypes.byref(ok), ctypes.byref(ov))
+        err = lib.b200_msb_sort_bits(_ptr(dev_keys), _ptr(dev_values), key_count, _ptr(dev_sorted_keys_out), _ptr(dev_sorted_values_out),
+                                     kt, vb, begin_bit, end_bit, _ptr(workspace), ctypes.byref(nbytes), _stream(stream), ctypes.byref(ok), ctypes.byref(ov))
     _check(err, "b200_msb_sort")
     keys = dev_keys if ok.value == dev_keys.data_ptr() or key_count == 0 else dev_sorted_keys_out
     vals = None

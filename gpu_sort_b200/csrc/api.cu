@@ -175,27 +175,34 @@ int b200_lsb_sort(void* d_temp, size_t* temp_bytes, void* d_keys_current, void* 
                                                     allow_overwrite, s)));
 }
 
-int b200_msb_sort(void* d_keys, void* d_values, uint64_t num_items, void* d_keys_alt, void* d_values_alt, int key_type,
-                  int value_bytes, void* d_workspace, size_t* workspace_bytes, b200_stream_t stream, void** out_keys,
-                  void** out_values) {
+int b200_msb_sort_bits(void* d_keys, void* d_values, uint64_t num_items, void* d_keys_alt, void* d_values_alt, int key_type,
+                       int value_bytes, int begin_bit, int end_bit, void* d_workspace, size_t* workspace_bytes, b200_stream_t stream,
+                       void** out_keys, void** out_values) {
   Twiddle tw; int kb;
   if (!make_twiddle(key_type, 0, &tw, &kb)) return (int)cudaErrorInvalidValue;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (d_workspace == nullptr && workspace_bytes == nullptr) {
     // reference default: temporary memory lives and dies inside the call (stream-ordered here, no host sync)
     size_t ws = 0;
-    int e = b200_msb_sort(nullptr, nullptr, num_items, nullptr, nullptr, key_type, value_bytes, nullptr, &ws, stream, nullptr, nullptr);
+    int e = b200_msb_sort_bits(nullptr, nullptr, num_items, nullptr, nullptr, key_type, value_bytes, begin_bit, end_bit, nullptr, &ws, stream, nullptr, nullptr);
     if (e) return e;
     void* w = nullptr;
     cudaError_t ce = cudaMallocAsync(&w, ws, s);
     if (ce != cudaSuccess) return (int)ce;
-    e = b200_msb_sort(d_keys, d_values, num_items, d_keys_alt, d_values_alt, key_type, value_bytes, w, &ws, stream, out_keys, out_values);
+    e = b200_msb_sort_bits(d_keys, d_values, num_items, d_keys_alt, d_values_alt, key_type, value_bytes, begin_bit, end_bit, w, &ws, stream, out_keys, out_values);
     ce = cudaFreeAsync(w, s);
     return e ? e : (int)ce;
   }
   if (workspace_bytes == nullptr) return (int)cudaErrorInvalidValue;
   DISPATCH_KV(kb, value_bytes, (msb_sort_impl<K, V>(d_keys, d_values, num_items, d_keys_alt, d_values_alt, tw, d_workspace,
-                                                    workspace_bytes, s, out_keys, out_values)));
+                                                    workspace_bytes, s, out_keys, out_values, begin_bit, end_bit)));
+}
+
+int b200_msb_sort(void* d_keys, void* d_values, uint64_t num_items, void* d_keys_alt, void* d_values_alt, int key_type,
+                  int value_bytes, void* d_workspace, size_t* workspace_bytes, b200_stream_t stream, void** out_keys,
+                  void** out_values) {
+  return b200_msb_sort_bits(d_keys, d_values, num_items, d_keys_alt, d_values_alt, key_type, value_bytes, 0, 64, d_workspace, workspace_bytes, stream,
+                            out_keys, out_values);
 }
 
 int b200_msb_sort_host(const void* h_keys, const void* h_values, uint64_t num_items, void* h_sorted_keys, void* h_sorted_values,

@@ -129,6 +129,41 @@ struct LocalItem {      // a bucket (or merged run of tiny buckets) that is fini
   uint16_t src;         // which of the two ping-pong buffers currently holds the bucket
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Destination of a key in the multi-GPU range partition: part = #{ j : splitters[j] <= bucket }, bucket = top `bits` bits.
+// A 256-entry table over the top 8 bits of the bucket answers it with one shared-memory load; only the (at most 15) coarse
+// cells that contain a splitter in their interior fall back to comparing against the splitters.
+// ---------------------------------------------------------------------------------------------------------
+struct RangeLut {
+  uint32_t split[16];
+  uint8_t lut[256];       // low 4 bits: part of the first bucket of the cell; bit 7: a splitter lies inside the cell
+  int cshift;             // bucket >> cshift = coarse cell
+};
+__device__ __forceinline__ void range_lut_build(RangeLut& r, const uint32_t* splitters, int num_parts, int bits) {
+  const unsigned tid = threadIdx.x;
+  const int cshift = bits > 8 ? bits - 8 : 0;
+  if (tid < 256) {
+    const uint32_t first = tid << cshift, last = ((tid + 1u) << cshift) - 1u;
+    uint32_t d = 0, inside = 0;
+    for (int j = 0; j < num_parts - 1; ++j) {
+      const uint32_t sp = splitters[j];
+      d += sp <= first ? 1u : 0u;
+      inside |= (sp > first && sp <= last) ? 1u : 0u;
+    }
+    r.lut[tid] = (uint8_t)(d | (inside << 7));
+  }
+  if (tid < 16) r.split[tid] = (int)tid < num_parts - 1 ? splitters[tid] : 0xFFFFFFFFu;
+  if (tid == 0) r.cshift = cshift;
+}
+__device__ __forceinline__ uint32_t range_part(const RangeLut& r, uint32_t bucket, int cshift) {
+  const uint32_t e = r.lut[bucket >> cshift];
+  if (!(e & 0x80u)) return e;
+  uint32_t d = 0;
+#pragma unroll
+  for (int j = 0; j < 15; ++j) d += bucket >= r.split[j] ? 1u : 0u;
+  return d;
+}
+
 template <int VB> struct ValType { using type = uint32_t; };
 template <> struct ValType<8> { using type = uint64_t; };
 

@@ -108,20 +108,16 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
   const int shift = a.shift; const uint32_t mask = a.mask;
   const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
   using S = typename std::make_signed<K>::type;
-  __shared__ uint32_t split[16];
+  __shared__ RangeLut rl;
   const bool range = a.splitters != nullptr;
-  if (range && tid < 16) split[tid] = (int)tid < a.num_parts - 1 ? a.splitters[tid] : 0xFFFFFFFFu;
+  if (range) range_lut_build(rl, a.splitters, a.num_parts, (int)sizeof(K) * 8 - shift);
   __syncthreads();
+  const int cshift = range ? rl.cshift : 0;
   auto count = [&](K k) {
     if (a.tw_in) k = (K)(k ^ (((K)((S)k >> (sizeof(K) * 8 - 1)) & fl) | sg) ^ fp);
     uint32_t d;
     if (!range) d = digit_of<K>(k, shift, mask);
-    else {
-      const uint32_t b = (uint32_t)(k >> shift);
-      d = 0;
-#pragma unroll
-      for (int j = 0; j < 15; ++j) d += (j < a.num_parts - 1 && b >= split[j]) ? 1u : 0u;
-    }
+    else d = range_part(rl, (uint32_t)(k >> shift), cshift);
     atomicAdd(&sh[d], 1u);
   };
   for (uint32_t g = blockIdx.x; g < num_groups; g += gridDim.x) {

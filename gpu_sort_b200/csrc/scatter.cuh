@@ -81,18 +81,14 @@ struct ScatterSmem {
   uint32_t scratch[8];
   alignas(8) uint64_t bar[2];
   TileGeom geom[2];
-  uint32_t split[MAX_PARTS];
+  RangeLut range;
   uint32_t skewed;                                  // MSB: the previous tile had a dominant digit -> aggregate per warp
 };
 
 template <typename K, int MODE>
-__device__ __forceinline__ uint32_t scatter_digit(K k, int shift, uint32_t mask, const uint32_t* split, int num_parts) {
+__device__ __forceinline__ uint32_t scatter_digit(K k, int shift, uint32_t mask, const RangeLut& rl, int cshift) {
   if (MODE != MODE_RANGE) return digit_of<K>(k, shift, mask);
-  const uint32_t b = (uint32_t)(k >> shift);
-  uint32_t d = 0;
-#pragma unroll
-  for (int j = 0; j < MAX_PARTS - 1; ++j) d += (j < num_parts - 1 && b >= split[j]) ? 1u : 0u;
-  return d;
+  return range_part(rl, (uint32_t)(k >> shift), cshift);
 }
 
 // 32-bit / 64-bit forms of the order-preserving transform with the masks already narrowed to K (3 instructions).
@@ -165,6 +161,7 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
   const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
   const uint32_t cnt = FULL ? (uint32_t)TILE : g.cnt;
   const int shift = a.shift; const uint32_t mask = a.mask;
+  const int cshift = MODE == MODE_RANGE ? sm.range.cshift : 0;
   K* __restrict__ st = &sm.stage[slot][0];
   V* __restrict__ vst = &sm.vstage[VB ? slot : 0][0];
 
@@ -230,10 +227,29 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
     __syncthreads();
     uint16_t* wc = sm.wcnt + w * RADIX;
     const unsigned lt = (1u << lane) - 1u, lbit = 1u << lane;
+    if (MODE == MODE_RANGE) {
+      // few destinations: same-address atomics would serialise, so the lanes of a row find their peers with one ballot per
+      // destination instead (uniform loop over num_parts <= 16)
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        const unsigned d = scatter_digit<K, MODE>(key[j], shift, mask, sm.range, cshift);
+        unsigned peers = 0;
+        for (int p = 0; p < a.num_parts; ++p) {
+          const unsigned m = __ballot_sync(0xffffffffu, d == (unsigned)p);
+          if (d == (unsigned)p) peers = m;
+        }
+        const unsigned below = __popc(peers & lt);
+        unsigned b = 0;
+        if (below == 0) { b = wc[d]; wc[d] = (uint16_t)(b + __popc(peers)); }
+        b = __shfl_sync(0xffffffffu, b, __ffs(peers) - 1);
+        pos[j] = b + below;
+        __syncwarp();
+      }
+    } else {
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       uint32_t* wm = sm.match[j & 1] + w * RADIX;
-      const unsigned d = scatter_digit<K, MODE>(key[j], shift, mask, sm.split, a.num_parts);   // padding keys (all ones) rank last
+      const unsigned d = scatter_digit<K, MODE>(key[j], shift, mask, sm.range, cshift);   // padding keys (all ones) rank last
       atomicOr(&wm[d], lbit);
       __syncwarp();
       const unsigned peers = wm[d];
@@ -244,11 +260,12 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
       b = __shfl_sync(0xffffffffu, b, __ffs(peers) - 1);
       pos[j] = b + below;
     }
+    }
     __syncthreads();
     if (tid < RADIX) {
 #pragma unroll
       for (int ww = 0; ww < WARPS; ++ww) my_total += sm.wcnt[ww * RADIX + tid];
-      if (!FULL && tid == scatter_digit<K, MODE>((K)~(K)0, shift, mask, sm.split, a.num_parts)) my_total -= (uint32_t)TILE - cnt;   // padding
+      if (!FULL && tid == scatter_digit<K, MODE>((K)~(K)0, shift, mask, sm.range, cshift)) my_total -= (uint32_t)TILE - cnt;   // padding
     }
   }
 
@@ -310,7 +327,7 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
     const uint16_t* wc = sm.wcnt + w * RADIX;
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-      pos[j] += wc[scatter_digit<K, MODE>(key[j], shift, mask, sm.split, a.num_parts)];
+      pos[j] += wc[scatter_digit<K, MODE>(key[j], shift, mask, sm.range, cshift)];
       if (FULL || pos[j] < cnt) st[pos[j]] = key[j];        // padding keys rank after every real key: pos >= cnt
     }
   }
@@ -354,7 +371,7 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
       const uint32_t p = j * THREADS + tid;
       if (FULL || p < cnt) {
         const K k = st[p];
-        const uint32_t d = scatter_digit<K, MODE>(k, shift, mask, sm.split, a.num_parts);
+        const uint32_t d = scatter_digit<K, MODE>(k, shift, mask, sm.range, cshift);
         st_global<K>(sm.kptr[d], p, tw_apply_out<K>(k, sg, fl, fp));
         if (VB) st_global<V>(sm.vptr[d], p, vst[p]);
       }
@@ -365,7 +382,7 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
       const uint32_t p = j * THREADS + tid;
       if (FULL || p < cnt) {
         const K k = st[p];
-        const uint32_t d = scatter_digit<K, MODE>(k, shift, mask, sm.split, a.num_parts);
+        const uint32_t d = scatter_digit<K, MODE>(k, shift, mask, sm.range, cshift);
         st_global<K>(sm.kptr[d], p, k);
         if (VB) st_global<V>(sm.vptr[d], p, vst[p]);
       }
@@ -445,7 +462,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_kernel(const __grid_cons
     stage_tile(0, t0, td);
   }
   if (tid == 0) sm.skewed = 0;
-  if (MODE == MODE_RANGE && tid < MAX_PARTS) sm.split[tid] = (int)tid < a.num_parts - 1 ? a.splitters[tid] : 0xFFFFFFFFu;
+  if (MODE == MODE_RANGE) range_lut_build(sm.range, a.splitters, a.num_parts, (int)sizeof(K) * 8 - a.shift);
   __syncthreads();
 
   for (uint32_t it = 0;; ++it) {

@@ -25,7 +25,7 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
 
 template <typename K, int VB>
 cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, void* vals_alt, const Twiddle& tw,
-                          void* d_ws, size_t* ws_bytes, cudaStream_t s, void** out_keys, void** out_vals);
+                          void* d_ws, size_t* ws_bytes, cudaStream_t s, void** out_keys, void** out_vals, int begin_bit, int end_bit);
 
 template <typename K, int VB>
 cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* kin, const void* vin, void* kout, void* vout,

@@ -356,15 +356,18 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
 // ===============================================================================================================
 template <typename K, int VB>
 cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, void* vals_alt, const Twiddle& tw,
-                          void* d_ws, size_t* ws_bytes, cudaStream_t s, void** out_keys, void** out_vals) {
+                          void* d_ws, size_t* ws_bytes, cudaStream_t s, void** out_keys, void** out_vals, int begin_bit, int end_bit) {
   constexpr int KEY_BITS = sizeof(K) * 8;
-  constexpr int LEVELS = sizeof(K);
+  if (begin_bit < 0) begin_bit = 0;
+  if (end_bit > KEY_BITS) end_bit = KEY_BITS;
+  if (end_bit < begin_bit) end_bit = begin_bit;
+  const int LEVELS = (end_bit - begin_bit + 7) / 8;
   if (out_keys) *out_keys = keys;
   if (out_vals) *out_vals = vals;
 
   if (n >= (1ull << 32)) {     // beyond the 32-bit tile offsets: the stable LSD engine gives a valid result
     int sel = 0;
-    cudaError_t e = lsb_sort_impl<K, VB>(d_ws, ws_bytes, keys, keys_alt, vals, vals_alt, &sel, n, tw, 0, KEY_BITS, 1, s);
+    cudaError_t e = lsb_sort_impl<K, VB>(d_ws, ws_bytes, keys, keys_alt, vals, vals_alt, &sel, n, tw, begin_bit, end_bit, 1, s);
     if (d_ws && e == cudaSuccess && sel) { if (out_keys) *out_keys = keys_alt; if (out_vals) *out_vals = vals_alt; }
     return e;
   }
@@ -375,10 +378,11 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
   if (*ws_bytes < cv.total()) return cudaErrorInvalidValue;
   if (n == 0) return cudaSuccess;
   void* bufk[3] = {keys, keys_alt, nullptr}; void* bufv[3] = {vals, vals_alt, nullptr};
-  const int fin = LEVELS & 1;               // 4 / 8 levels: the last level lands in the input buffer, like the reference
+  const int fin = (n <= (uint64_t)Cfg<K, VB>::LOCAL_CAP) ? 0 : (LEVELS & 1);   // 4 / 8 levels: the last level lands in the input buffer, like the reference
   if (out_keys) *out_keys = bufk[fin];
   if (out_vals) *out_vals = bufv[fin];
-  return msd_sort_run<K, VB, false>(w, bufk, bufv, 2, fin, n, tw, 0, KEY_BITS, s);
+  if (LEVELS == 0) return cudaSuccess;
+  return msd_sort_run<K, VB, false>(w, bufk, bufv, 2, fin, n, tw, begin_bit, end_bit, s);
 }
 
 // ===============================================================================================================

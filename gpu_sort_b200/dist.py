@@ -268,15 +268,25 @@ class DistSorter:
         else:
             self.sort_temp = torch.empty(gs.rdxsrt_workspace_bytes(self.cap, self.kt, vb), dtype=torch.uint8, device=dev)
 
-    def sort(self, keys: torch.Tensor, vals: Optional[torch.Tensor] = None):
+    def sort(self, keys: torch.Tensor, vals: Optional[torch.Tensor] = None, profile: bool = False):
         gs, G, rank, bits = self.gs, self.G, self.rank, self.bits
         n = keys.numel()
         stream = gs._stream(None)
+        marks = []
+
+        def mark(name):
+            if profile:
+                e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e))
+        if profile:
+            gs.prof_enable(True)
+        mark("start")
         gs._check(gs.lib.b200_msd_histogram(gs._ptr(keys), n, self.kt, bits, gs._ptr(self.counts), stream), "b200_msd_histogram")       # 1
         glob = self.counts
         if G > 1:
             glob = self.counts.clone()
+            mark("histogram")
             dist.all_reduce(glob, group=self.group)                                                                                   # 2
+        mark("allreduce")
         sp = choose_splitters_tensor(glob, G)                                                                                         # 3 (device)
         spp = torch.cat([sp, sp.new_zeros(1)])
         mine = part_counts(self.counts, sp, G)                                                                                        # 5
@@ -287,21 +297,32 @@ class DistSorter:
         else:
             mat = mine.view(1, 1)
         base = mat[:rank].sum(0) if rank > 0 else torch.zeros(G, dtype=torch.int64, device=keys.device)      # my start inside every destination
-        matrix = mat.cpu().numpy()                                   # the one host sync: n_recv sizes the local sort
+        mark("splitters+counts")
+        host = torch.cat([mat.reshape(-1), sp.to(torch.int64)]).cpu().numpy()     # the one host sync: n_recv sizes the local sort
+        matrix = host[:G * G].reshape(G, G)
         send, recv, n_recv = receive_layout(matrix, rank)
+        # every key this rank receives lies in [lo, hi]: the leading bits on which lo and hi agree need not be sorted
+        kbits = gs.KEY_BYTES[self.kt] * 8
+        lo = (int(host[G * G + rank - 1]) if rank > 0 else 0) << (kbits - bits)
+        hi = (((int(host[G * G + rank]) if rank < G - 1 else (1 << bits)) << (kbits - bits)) - 1) if G > 1 else (1 << kbits) - 1
+        end_bit = max((lo ^ max(hi, lo)).bit_length(), 1)
         if n_recv > self.cap:
             raise RuntimeError(f"rank {rank}: {n_recv} keys to receive exceed the receive capacity {self.cap} (key range too skewed for range partitioning)")
         nb = ctypes.c_size_t(self.part_temp.numel())
         if self.fused:
             self.hk.barrier()                                        # every peer is done with the previous contents of its receive buffer
+            mark("d2h+barrier")
             gs._check(gs.lib.b200_range_partition_to(gs._ptr(self.part_temp), ctypes.byref(nb), gs._ptr(keys), gs._ptr(vals), n, self.kt, self.vb, bits,
                                                      gs._ptr(spp), G, gs._ptr(self.counts), gs._ptr(self.offs), gs._ptr(self.dst_k), gs._ptr(self.dst_v),
                                                      gs._ptr(base.contiguous()), stream), "b200_range_partition_to")                  # 4 + 6 fused
+            mark("partition_fused")
             self.hk.barrier()                                        # all peers' stores have landed
+            mark("barrier")
         else:
             gs._check(gs.lib.b200_range_partition(gs._ptr(self.part_temp), ctypes.byref(nb), gs._ptr(keys), gs._ptr(vals), gs._ptr(self.send_k),
                                                   gs._ptr(self.send_v), n, self.kt, self.vb, bits, gs._ptr(spp), G, gs._ptr(self.counts), gs._ptr(self.offs),
                                                   stream), "b200_range_partition")                                                    # 4
+            mark("partition")
             if G > 1:
                 dist.all_to_all_single(self.recv_k[:n_recv], self.send_k, output_split_sizes=recv, input_split_sizes=send, group=self.group)   # 6
                 if self.pairs:
@@ -310,14 +331,23 @@ class DistSorter:
                 self.recv_k[:n].copy_(self.send_k)
                 if self.pairs:
                     self.recv_v[:n].copy_(self.send_v)
+        mark("exchange")
         rk = self.recv_k[:n_recv]; rv = self.recv_v[:n_recv] if self.pairs else None
         if n_recv == 0:
             sk, sv = rk, rv
         elif self.stable:                                                                                                             # 7
             dk = gs.DoubleBuffer(rk, self.alt_k[:n_recv]); dv = gs.DoubleBuffer(rv, self.alt_v[:n_recv]) if self.pairs else None
-            gs.DeviceRadixSort._run(self.sort_temp, dk, dv, n_recv, 0, None, False, None, self.kt)
+            gs.DeviceRadixSort._run(self.sort_temp, dk, dv, n_recv, 0, end_bit, False, None, self.kt)
             sk, sv = dk.Current(), (dv.Current() if self.pairs else None)
         else:
-            r = gs.rdxsrt_unstable_sort(rk, rv, n_recv, self.alt_k[:n_recv], self.alt_v[:n_recv] if self.pairs else None, workspace=self.sort_temp, key_type=self.kt)
+            r = gs.rdxsrt_unstable_sort(rk, rv, n_recv, self.alt_k[:n_recv], self.alt_v[:n_recv] if self.pairs else None, workspace=self.sort_temp, key_type=self.kt,
+                                        end_bit=end_bit)
             sk, sv = r.sorted_keys, r.sorted_values
-        return sk, sv, {"count": n_recv, "count_matrix": matrix, "imbalance": imbalance(matrix), "fused": self.fused}
+        mark("local_sort")
+        info = {"count": n_recv, "count_matrix": matrix, "imbalance": imbalance(matrix), "fused": self.fused}
+        if profile:
+            torch.cuda.synchronize()
+            info["kernels_ms"] = {k: round(v[1], 3) for k, v in gs.prof_report().items()}
+            gs.prof_enable(False)
+            info["phases_ms"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 3) for i in range(1, len(marks))}
+        return sk, sv, info

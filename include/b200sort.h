@@ -94,6 +94,15 @@ B200_API int b200_msb_sort(void* d_keys, void* d_values, uint64_t num_items,
                   void* d_workspace, size_t* workspace_bytes, b200_stream_t stream,
                   void** out_keys, void** out_values);
 
+/* b200_msb_sort restricted to key bits [begin_bit, end_bit) of the order-transformed key (the counterpart of the bit range of
+ * cub::DeviceRadixSort, device_radix_sort.cuh:154-157).  The multi-GPU path uses it: after the key-range exchange the leading
+ * bits of every key a GPU holds are known to be equal.  The result lands in the input buffers when ceil((end-begin)/8) is even. */
+B200_API int b200_msb_sort_bits(void* d_keys, void* d_values, uint64_t num_items,
+                       void* d_keys_alt, void* d_values_alt,
+                       int key_type, int value_bytes, int begin_bit, int end_bit,
+                       void* d_workspace, size_t* workspace_bytes, b200_stream_t stream,
+                       void** out_keys, void** out_values);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Host-pointer convenience wrappers (allocate device buffers, H2D, sort, D2H, free; synchronous).
  * Replace rdxsrt_unstable_sort_keys / rdxsrt_unstable_sort_pairs  msb/src/sort/gpu_radix_sort.h:510-541, 543-587
