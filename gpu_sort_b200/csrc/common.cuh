@@ -91,18 +91,22 @@ __device__ __forceinline__ unsigned match_digit(unsigned d) {
 __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* scratch) {
   const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   uint32_t inc = v;
+  if (w < 8) {                        // warp-uniform: only the eight digit-owner warps take part
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= (unsigned)o) inc += t;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) scratch[w] = inc;
   }
-  if (w < 8 && lane == 31) scratch[w] = inc;
   __syncthreads();
   uint32_t woff = 0;
+  if (w < 8) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint32_t s = scratch[j];
-    if ((unsigned)j < w) woff += s;
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t s = scratch[j];
+      if ((unsigned)j < w) woff += s;
+    }
   }
   __syncthreads();
   return woff + inc - v;

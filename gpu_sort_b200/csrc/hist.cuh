@@ -98,7 +98,7 @@ struct TileHistArgs {
   const uint32_t* splitters; int num_parts;     // range mode: digit = #{ j < num_parts-1 : splitters[j] <= (key >> shift) }
 };
 
-template <typename K>
+template <typename K, bool RANGE>
 __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_constant__ TileHistArgs a) {
   __shared__ uint32_t sh[RADIX];
   const K* __restrict__ keys = reinterpret_cast<const K*>(a.keys);
@@ -109,14 +109,12 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
   const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
   using S = typename std::make_signed<K>::type;
   __shared__ RangeLut rl;
-  const bool range = a.splitters != nullptr;
-  if (range) range_lut_build(rl, a.splitters, a.num_parts, (int)sizeof(K) * 8 - shift);
-  __syncthreads();
-  const int cshift = range ? rl.cshift : 0;
+  if (RANGE) { range_lut_build(rl, a.splitters, a.num_parts, (int)sizeof(K) * 8 - shift); __syncthreads(); }
+  const int cshift = RANGE ? rl.cshift : 0;
   auto count = [&](K k) {
     if (a.tw_in) k = (K)(k ^ (((K)((S)k >> (sizeof(K) * 8 - 1)) & fl) | sg) ^ fp);
     uint32_t d;
-    if (!range) d = digit_of<K>(k, shift, mask);
+    if (!RANGE) d = digit_of<K>(k, shift, mask);
     else d = range_part(rl, (uint32_t)(k >> shift), cshift);
     atomicAdd(&sh[d], 1u);
   };

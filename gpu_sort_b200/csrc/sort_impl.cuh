@@ -71,7 +71,7 @@ inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cud
   using C = Cfg<K, VB>;
   auto kernel = scatter_kernel<K, VB, C::THREADS, C::IPT, C::OCC, MODE, ORD>;
   constexpr size_t smem = sizeof(ScatterSmem<K, VB, C::THREADS, C::IPT, MODE, ORD>);
-  static_assert(smem <= 113 * 1024, "at least two scatter CTAs must fit one SM (228 KB of shared memory)");
+  static_assert(smem <= (C::OCC >= 2 ? 113 : 227) * 1024, "the scatter CTAs of one SM must fit its 228 KB of shared memory");
   static int grid = 0;
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
@@ -163,6 +163,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   using C = Cfg<K, VB>;
   const int levels = (end_bit - begin_bit + 7) / 8;
   const int sms = num_sms();
+  const int twid = (tw.sign_mask | tw.float_mask | tw.flip_mask) != 0 ? 1 : 0;     // unsigned ascending keys: the transform is the identity
   MsbCounters* ctr = w.ctr;
   // level L scatters from in_buf(L) to out_buf(L); the LAST possible level must land in `fin`
   auto out_buf = [&](int L) -> int {
@@ -176,11 +177,11 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
   la.items = w.locals[0]; la.num_items_ptr = &ctr->num_locals[0];
   la.overflow = w.locals[2]; la.num_overflow_ptr = &ctr->num_overflow;
-  la.tw_out = 1; la.begin_bit = begin_bit; la.tw = tw;
+  la.tw_out = twid; la.begin_bit = begin_bit; la.tw = tw;
 
   if (n <= (uint64_t)C::LOCAL_CAP) {     // fits one CTA: a single on-chip sort straight into the final buffer
     single_item_kernel<<<1, 1, 0, s>>>(w.locals[0], &ctr->num_locals[0], (uint32_t)n, end_bit);
-    la.tw_in = 1;
+    la.tw_in = twid;
     return launch_local<K, VB, ALGO_LSD, ORDERED>(la, 1, s);
   }
 
@@ -203,9 +204,9 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     TileHistArgs ha{};
     ha.keys = bufk[ib]; ha.descs = w.descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
     ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist;
-    ha.shift = shift; ha.mask = mask; ha.tw_in = (L == 0); ha.tw = tw;
+    ha.shift = shift; ha.mask = mask; ha.tw_in = (L == 0) ? twid : 0; ha.tw = tw;
     const int hgrid = (int)std::min<uint32_t>(w.max_groups, (uint32_t)sms * 4);
-    { ProfScope prof("tile_hist", s); tile_hist_kernel<K><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
+    { ProfScope prof("tile_hist", s); tile_hist_kernel<K, false><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
     { ProfScope prof("msb_sched", s); group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(w.group_tail, w.group_flag, w.carry, &ctr->num_tiles[L]); }
 
     ClassifyArgs ca{};
@@ -224,7 +225,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     pa.keys_in = bufk[ib]; pa.keys_out = bufk[ob]; pa.vals_in = bufv[ib]; pa.vals_out = bufv[ob];
     pa.descs = w.descs; pa.num_tiles_ptr = &ctr->num_tiles[L];
     pa.bins = w.bins; pa.tile_off = w.tile_off; pa.carry = w.carry;
-    pa.shift = shift; pa.mask = mask; pa.tw_in = (L == 0); pa.tw_out = (shift == begin_bit); pa.tw = tw;
+    pa.shift = shift; pa.mask = mask; pa.tw_in = (L == 0) ? twid : 0; pa.tw_out = (shift == begin_bit) ? twid : 0; pa.tw = tw;
     B200_CHECK((launch_scatter<K, VB, MODE_SEG, ORDERED>(pa, w.max_tiles, s)));
 
     if (L + 1 < levels) {
@@ -452,7 +453,7 @@ cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* k
   ha.keys = kin; ha.descs = descs; ha.num_tiles_ptr = &ctr->num_tiles[0];
   ha.tile_off = tile_off; ha.group_tail = group_tail; ha.group_flag = group_flag; ha.seg_hist = seg_hist;
   ha.shift = KEY_BITS - bits; ha.mask = 0xFFu; ha.tw_in = 1; ha.tw = tw; ha.splitters = d_splitters; ha.num_parts = num_parts;
-  { ProfScope prof("tile_hist", s); tile_hist_kernel<K><<<(int)std::min<uint32_t>(max_groups, (uint32_t)sms * 4), HIST_THREADS, 0, s>>>(ha); }
+  { ProfScope prof("tile_hist", s); tile_hist_kernel<K, true><<<(int)std::min<uint32_t>(max_groups, (uint32_t)sms * 4), HIST_THREADS, 0, s>>>(ha); }
   group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(group_tail, group_flag, carry, &ctr->num_tiles[0]);
   ScatterArgs pa{};
   pa.keys_in = kin; pa.keys_out = kout; pa.vals_in = vin; pa.vals_out = vout;

@@ -20,12 +20,13 @@ if [ -x oracle/_ref/msb_gtests_on_b200sort ]; then
   LD_LIBRARY_PATH=gpu_sort_b200 timeout 600 oracle/_ref/msb_gtests_on_b200sort --gtest_filter='Sort_Keys.Entropy_*:Sort_Pairs.*' -k 200000 -p 100000 > gpurun_out/ref_gtests_on_b200sort.log 2>&1; grep -E "PASSED|FAILED|tests ran" gpurun_out/ref_gtests_on_b200sort.log | tail -5
 fi
 if [ "${1:-}" = "ncu" ]; then
+  # bounded captures: tools/one_sort.py runs 2 sorts; the launch list sees both, the full capture only the second sort's
+  # data-moving kernels (skip the first sort's launches of the same families: 4 levels x (hist + scatter) + 3 on-chip = 11)
   for w in cfg2 cfg3; do
-    python bench.py --workload $w --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/plain_$w.log 2>&1 &&
-    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$w.csv \
-        python bench.py --workload $w --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_launches_$w.log 2>&1
-    ncu --set full --clock-control none --import-source on -k regex:"scatter_kernel|local_sort_kernel|tile_hist_kernel" -f -o gpurun_out/prof_$w \
-        python bench.py --workload $w --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full_$w.log 2>&1
+    python tools/one_sort.py $w > gpurun_out/plain_$w.log 2>&1 &&
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$w.csv python tools/one_sort.py $w > gpurun_out/ncu_launches_$w.log 2>&1
+    ncu --set full --clock-control none --import-source on -k regex:"scatter_kernel|local_sort_kernel|tile_hist_kernel" -s 11 -c 11 -f -o gpurun_out/prof_$w \
+        python tools/one_sort.py $w > gpurun_out/ncu_full_$w.log 2>&1
   done
 fi
 echo done

@@ -8,14 +8,18 @@ usage: make_profiles.py ROUND TAG WORKLOAD SORTS_CAPTURED   e.g.  make_profiles.
 import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rnd, tag, workload, sorts = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
-FAM = [("scatter_kernel", "(int)0, (bool)0", "scatter"), ("scatter_kernel", "(int)0, (bool)1", "scatter_stable"), ("scatter_kernel", "(int)1,", "scatter_onesweep"),
-       ("scatter_kernel", "(int)2,", "range_partition"), ("tile_hist_kernel", "", "tile_hist"), ("hist_all_kernel", "", "hist_all"),
-       ("local_sort_kernel", "(int)0, (bool)", "local_sort_lsd"), ("local_sort_kernel", "(int)1, (bool)", "local_sort_count")]
+import re
 def family(name):
-    for a, b, f in FAM:
-        if a in name and (b in name or not b):
-            return f
-    return "msb_sched" if "b200::" in name or "_kernel" in name and "at::" not in name else None
+    """kernel family as bench.py / b200_prof_report name it, from a (possibly abbreviated) demangled kernel name"""
+    args = [x.strip().split(")")[-1] for x in re.sub(r"^[^<]*<", "", name).split(">")[0].split(",")]
+    if "scatter_kernel" in name and len(args) >= 7:
+        mode, ord_ = args[5], args[6]
+        return {"0": "scatter_stable" if ord_ in ("1", "true") else "scatter", "1": "scatter_onesweep", "2": "range_partition"}.get(mode, "scatter")
+    if "local_sort_kernel" in name and len(args) >= 6:
+        return "local_sort_count" if args[4] == "1" else "local_sort_lsd"
+    if "tile_hist_kernel" in name: return "tile_hist"
+    if "hist_all_kernel" in name: return "hist_all"
+    return None
 
 lc = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 if os.path.exists(lc):
