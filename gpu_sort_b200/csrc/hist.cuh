@@ -96,9 +96,10 @@ struct TileHistArgs {
   uint32_t* seg_hist;
   int shift; uint32_t mask; int tw_in; Twiddle tw;
   const uint32_t* splitters; int num_parts;     // range mode: digit = #{ j < num_parts-1 : splitters[j] <= (key >> shift) }
+  unsigned long long* key_or; unsigned long long* key_and;   // PROBE: OR / AND of all transformed keys are accumulated here
 };
 
-template <typename K, bool RANGE>
+template <typename K, bool RANGE, bool PROBE>
 __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_constant__ TileHistArgs a) {
   __shared__ uint32_t sh[RADIX];
   const K* __restrict__ keys = reinterpret_cast<const K*>(a.keys);
@@ -111,8 +112,10 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
   __shared__ RangeLut rl;
   if (RANGE) { range_lut_build(rl, a.splitters, a.num_parts, (int)sizeof(K) * 8 - shift); __syncthreads(); }
   const int cshift = RANGE ? rl.cshift : 0;
+  K acc_or = (K)0, acc_and = (K)~(K)0;
   auto count = [&](K k) {
     if (a.tw_in) k = (K)(k ^ (((K)((S)k >> (sizeof(K) * 8 - 1)) & fl) | sg) ^ fp);
+    if (PROBE) { acc_or |= k; acc_and &= k; }
     uint32_t d;
     if (!RANGE) d = digit_of<K>(k, shift, mask);
     else d = range_part(rl, (uint32_t)(k >> shift), cshift);
@@ -167,6 +170,17 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
       if (acc) atomicAdd(&a.seg_hist[(uint64_t)cur_seg * RADIX + tid], acc);
       a.group_tail[(uint64_t)g * RADIX + tid] = run;
       if (tid == 0) a.group_flag[g] = flag;
+    }
+  }
+  if (PROBE) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc_or |= (K)__shfl_xor_sync(0xffffffffu, acc_or, o);
+      acc_and &= (K)__shfl_xor_sync(0xffffffffu, acc_and, o);
+    }
+    if ((tid & 31u) == 0) {
+      atomicOr(a.key_or, (unsigned long long)acc_or);
+      atomicAnd(a.key_and, (unsigned long long)acc_and | (sizeof(K) == 4 ? 0xFFFFFFFF00000000ull : 0ull));
     }
   }
 }

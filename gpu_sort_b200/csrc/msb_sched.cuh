@@ -21,12 +21,14 @@ struct MsbCounters {            // one small zero-initialised block in the works
   uint32_t num_overflow;        // buckets the counting sort handed back
   uint32_t error;
   uint32_t pad;
+  unsigned long long key_or, key_and;     // OR / AND of all transformed keys (level-0 histogram): bits where they agree are constant
 };
 
 static __global__ void msb_init_kernel(Seg* segs, MsbCounters* c, uint64_t n) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     segs[0].off = 0; segs[0].cnt = n;
     c->num_segs[0] = 1;
+    c->key_or = 0ull; c->key_and = ~0ull;
   }
 }
 

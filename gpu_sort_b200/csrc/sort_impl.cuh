@@ -157,29 +157,42 @@ inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
   for (int i = 0; i < 3; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
 }
 
+// Pinned 16-byte landing zone for the key-range probe (one per host thread).
+inline unsigned long long* probe_buffer() {
+  static thread_local unsigned long long* p = nullptr;
+  if (!p && cudaHostAlloc(reinterpret_cast<void**>(&p), 2 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+  return p;
+}
+constexpr uint64_t PROBE_MIN_ITEMS = 1ull << 22;     // below this the extra stream synchronisation costs more than it can save
+
+// fin_in: buffer the result must land in (-1: the engine picks bufk[levels & 1] of the two ping-pong buffers); *fin_out says where it is.
 template <typename K, int VB, bool ORDERED>
-cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const bufv[3], int nbuf, int fin, uint64_t n, const Twiddle& tw,
-                         int begin_bit, int end_bit, cudaStream_t s) {
+cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const bufv[3], int nbuf, int fin_in, int* fin_out, uint64_t n,
+                         const Twiddle& tw, int begin_bit, int end_bit, cudaStream_t s) {
   using C = Cfg<K, VB>;
-  const int levels = (end_bit - begin_bit + 7) / 8;
+  using V = typename ValType<VB>::type;
   const int sms = num_sms();
-  const int twid = (tw.sign_mask | tw.float_mask | tw.flip_mask) != 0 ? 1 : 0;     // unsigned ascending keys: the transform is the identity
   MsbCounters* ctr = w.ctr;
+  const int twid = (tw.sign_mask | tw.float_mask | tw.flip_mask) != 0 ? 1 : 0;     // unsigned ascending keys: the transform is the identity
+  int levels = (end_bit - begin_bit + 7) / 8;
+  int fin = fin_in >= 0 ? fin_in : (levels & 1);
   // level L scatters from in_buf(L) to out_buf(L); the LAST possible level must land in `fin`
   auto out_buf = [&](int L) -> int {
-    if (nbuf == 2) return (L + 1) & 1;
+    if (nbuf == 2) return fin_in >= 0 ? (((levels - 1 - L) & 1) == 0 ? fin : fin ^ 1) : (L + 1) & 1;
     return ((levels - 1 - L) & 1) == 0 ? fin : (fin == 1 ? 2 : 1);      // never the input buffer 0
   };
   auto in_buf = [&](int L) -> int { return L == 0 ? 0 : out_buf(L - 1); };
 
   LocalArgs la{};
   for (int i = 0; i < 3; ++i) { la.keys[i] = bufk[i < nbuf ? i : 0]; la.vals[i] = bufv[i < nbuf ? i : 0]; }
-  la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
   la.items = w.locals[0]; la.num_items_ptr = &ctr->num_locals[0];
   la.overflow = w.locals[2]; la.num_overflow_ptr = &ctr->num_overflow;
   la.tw_out = twid; la.begin_bit = begin_bit; la.tw = tw;
 
   if (n <= (uint64_t)C::LOCAL_CAP) {     // fits one CTA: a single on-chip sort straight into the final buffer
+    if (fin_in < 0) fin = 0;
+    if (fin_out) *fin_out = fin;
+    la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
     single_item_kernel<<<1, 1, 0, s>>>(w.locals[0], &ctr->num_locals[0], (uint32_t)n, end_bit);
     la.tw_in = twid;
     return launch_local<K, VB, ALGO_LSD, ORDERED>(la, 1, s);
@@ -191,6 +204,15 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     msb_init_kernel<<<1, 32, 0, s>>>(w.segs0, ctr, n);
     scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(w.segs0, &ctr->num_segs[0], w.tile_base, &ctr->num_tiles[0], w.max_tiles, &ctr->error, C::TILE);
     fill_descs_kernel<<<sms * 2, 256, 0, s>>>(w.segs0, w.tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], w.descs, C::TILE);
+  }
+  // Key-range probe: the level-0 histogram also ORs / ANDs every key.  Leading bits on which all keys agree cannot influence
+  // the order, so the digit windows start below them (small-range keys, e.g. indices below 2^20 in 64-bit keys, would
+  // otherwise spend whole sweeps on single-bucket levels).  Costs one 16-byte read-back + stream synchronisation; skipped for
+  // small inputs and while the stream is being captured into a CUDA graph.
+  bool probe = n >= PROBE_MIN_ITEMS && levels > 1;
+  if (probe) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone || probe_buffer() == nullptr) probe = false;
   }
   for (int L = 0; L < levels; ++L) {
     const int shift = std::max(begin_bit, end_bit - 8 * (L + 1));
@@ -205,8 +227,37 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     ha.keys = bufk[ib]; ha.descs = w.descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
     ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist;
     ha.shift = shift; ha.mask = mask; ha.tw_in = (L == 0) ? twid : 0; ha.tw = tw;
+    ha.key_or = &ctr->key_or; ha.key_and = &ctr->key_and;
     const int hgrid = (int)std::min<uint32_t>(w.max_groups, (uint32_t)sms * 4);
-    { ProfScope prof("tile_hist", s); tile_hist_kernel<K, false><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
+    if (L == 0 && probe) {
+      { ProfScope prof("tile_hist", s); tile_hist_kernel<K, false, true><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
+      unsigned long long* hp = probe_buffer();
+      B200_CHECK(cudaMemcpyAsync(hp, &ctr->key_or, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+      B200_CHECK(cudaStreamSynchronize(s));
+      probe = false;
+      unsigned long long diff = hp[0] ^ hp[1];                                  // bits on which the keys differ
+      diff &= (end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1ull)) & ~((1ull << begin_bit) - 1ull);
+      int new_end = begin_bit;
+      while (new_end < end_bit && (diff >> new_end) != 0) ++new_end;           // highest differing bit + 1
+      if (new_end < end_bit) {
+        // restart with the narrower window (the level-0 histogram just taken used the wrong digit)
+        end_bit = new_end;
+        levels = (end_bit - begin_bit + 7) / 8;
+        if (fin_in < 0) fin = levels & 1;
+        if (levels == 0) {                // all keys equal on the sorted bits: the input order is the (stable) answer
+          if (fin_out) *fin_out = fin;
+          if (fin != 0) {
+            B200_CHECK(cudaMemcpyAsync(bufk[fin], bufk[0], n * sizeof(K), cudaMemcpyDeviceToDevice, s));
+            if (VB) B200_CHECK(cudaMemcpyAsync(bufv[fin], bufv[0], n * sizeof(V), cudaMemcpyDeviceToDevice, s));
+          }
+          return cudaSuccess;
+        }
+        L = -1;
+        continue;
+      }
+    } else {
+      ProfScope prof("tile_hist", s); tile_hist_kernel<K, false, false><<<hgrid, HIST_THREADS, 0, s>>>(ha);
+    }
     { ProfScope prof("msb_sched", s); group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(w.group_tail, w.group_flag, w.carry, &ctr->num_tiles[L]); }
 
     ClassifyArgs ca{};
@@ -234,6 +285,8 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
       fill_descs_kernel<<<sms * 2, 256, 0, s>>>(nxt, w.tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], w.descs, C::TILE);
     }
   }
+  if (fin_out) *fin_out = fin;
+  la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
   la.tw_in = 0;
   B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
   if (end_bit - begin_bit > 24) {          // some level left more than 16 bits to its buckets
@@ -307,9 +360,10 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     void* bufk[3] = {k0, k1, k2}; void* bufv[3] = {v0, v1, v2};
     // two buffers: the last possible level lands in buffer (passes & 1), so that is where everything is finished
     // (DoubleBuffer semantics: the selector says where); pointer overloads always deliver into the alternate buffers
-    const int fin = (allow_overwrite && n > (uint64_t)C::LOCAL_CAP) ? (passes & 1) : 1;
+    int fin = 1;
+    const cudaError_t e = msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s);
     if (selector) *selector = fin;
-    return msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, fin, n, tw, begin_bit, end_bit, s);
+    return e;
   }
 
   // ---- onesweep LSD engine: all digit histograms in one read, then one look-back scatter launch per digit
@@ -379,11 +433,14 @@ cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, vo
   if (*ws_bytes < cv.total()) return cudaErrorInvalidValue;
   if (n == 0) return cudaSuccess;
   void* bufk[3] = {keys, keys_alt, nullptr}; void* bufv[3] = {vals, vals_alt, nullptr};
-  const int fin = (n <= (uint64_t)Cfg<K, VB>::LOCAL_CAP) ? 0 : (LEVELS & 1);   // 4 / 8 levels: the last level lands in the input buffer, like the reference
+  if (LEVELS == 0) return cudaSuccess;
+  // 4 / 8 levels: the last level lands in the input buffer, like the reference; fewer levels (bit sub-range, or leading bits
+  // found constant by the key-range probe) may leave the result in the alternate buffers -- out_keys / out_vals say where
+  int fin = 0;
+  const cudaError_t e = msd_sort_run<K, VB, false>(w, bufk, bufv, 2, -1, &fin, n, tw, begin_bit, end_bit, s);
   if (out_keys) *out_keys = bufk[fin];
   if (out_vals) *out_vals = bufv[fin];
-  if (LEVELS == 0) return cudaSuccess;
-  return msd_sort_run<K, VB, false>(w, bufk, bufv, 2, fin, n, tw, begin_bit, end_bit, s);
+  return e;
 }
 
 // ===============================================================================================================
@@ -453,7 +510,7 @@ cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* k
   ha.keys = kin; ha.descs = descs; ha.num_tiles_ptr = &ctr->num_tiles[0];
   ha.tile_off = tile_off; ha.group_tail = group_tail; ha.group_flag = group_flag; ha.seg_hist = seg_hist;
   ha.shift = KEY_BITS - bits; ha.mask = 0xFFu; ha.tw_in = 1; ha.tw = tw; ha.splitters = d_splitters; ha.num_parts = num_parts;
-  { ProfScope prof("tile_hist", s); tile_hist_kernel<K, true><<<(int)std::min<uint32_t>(max_groups, (uint32_t)sms * 4), HIST_THREADS, 0, s>>>(ha); }
+  { ProfScope prof("tile_hist", s); tile_hist_kernel<K, true, false><<<(int)std::min<uint32_t>(max_groups, (uint32_t)sms * 4), HIST_THREADS, 0, s>>>(ha); }
   group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(group_tail, group_flag, carry, &ctr->num_tiles[0]);
   ScatterArgs pa{};
   pa.keys_in = kin; pa.keys_out = kout; pa.vals_in = vin; pa.vals_out = vout;
