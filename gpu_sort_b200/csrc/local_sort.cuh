@@ -298,8 +298,7 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
     // ---- stable pass
     const int shift = lo + 8 * p;
     const uint32_t mask = (1u << (hi - shift < 8 ? hi - shift : 8)) - 1u;
-    uint4* z = reinterpret_cast<uint4*>(sm.match);
-    for (int i = tid; i < 2 * WARPS * RADIX / 4; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    // (the match masks are all zero here: zeroed once at kernel start, and every row's leader clears the word it used)
     uint4* zc = reinterpret_cast<uint4*>(sm.wcnt);
     for (int i = tid; i < WARPS * RADIX / 8; i += THREADS) zc[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -363,7 +362,7 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
 }
 
 template <typename K, int VB, int THREADS, int IPT, int ALGO, bool STABLE>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) local_sort_kernel(const __grid_constant__ LocalArgs a) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS <= 512 ? 2 : 1)) local_sort_kernel(const __grid_constant__ LocalArgs a) {
   using V = typename ValType<VB>::type;
   using SM = LocalSmem<K, VB, THREADS, IPT, ALGO>;
   constexpr unsigned PRODUCER = THREADS - 1;
@@ -397,6 +396,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) local_sort_
     }
   };
 
+  if (ALGO == ALGO_LSD) {
+    LsdSmem<THREADS>& ls = *reinterpret_cast<LsdSmem<THREADS>*>(&sm.rank);
+    uint4* z = reinterpret_cast<uint4*>(ls.match);
+    for (int i = tid; i < 2 * (THREADS / 32) * RADIX / 4; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
   // the producer knows its next item one iteration ahead, so the prefetch into the free slot goes out at the top
   LocalItem it_a{}, it_b{};
   if (tid == PRODUCER) {

@@ -220,8 +220,7 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, ScatterSmem<K
     // stable ranking.  Row j of a warp = its 32 keys j*32 .. j*32+31 of the warp's contiguous share; rows are ranked in
     // order, lanes in order inside a row.  Lanes with equal digits meet in match[j&1][w][d] (atomicOr of the lane bit);
     // the lowest such lane adds the row's count to the warp's running counter and hands the old value to its peers.
-    uint4* z = reinterpret_cast<uint4*>(sm.match);
-    for (int i = tid; i < 2 * WARPS * RADIX / 4; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    // (the match masks are all zero here: zeroed once at kernel start, and every row's leader clears the word it used)
     uint4* zc = reinterpret_cast<uint4*>(sm.wcnt);
     for (int i = tid; i < WARPS * RADIX / 8; i += THREADS) zc[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -462,6 +461,10 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_kernel(const __grid_cons
     stage_tile(0, t0, td);
   }
   if (tid == 0) sm.skewed = 0;
+  if (ORDERED) {
+    uint4* z = reinterpret_cast<uint4*>(sm.match);
+    for (int i = tid; i < 2 * SM::WARPS * RADIX / 4; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
   if (MODE == MODE_RANGE) range_lut_build(sm.range, a.splitters, a.num_parts, (int)sizeof(K) * 8 - a.shift);
   __syncthreads();
 

@@ -51,6 +51,10 @@ struct Cfg {
   static constexpr int LOCAL_IPT = sizeof(K) == 4 ? (VB == 8 ? 8 : B200_LOCAL_IPT32) : (VB == 0 ? 12 : 8);
   static constexpr int LOCAL_CAP = LOCAL_THREADS * LOCAL_IPT;
   static constexpr uint32_t MERGE_CAP = LOCAL_CAP / 4;  // runs of tiny neighbouring buckets are merged up to this size
+  // second on-chip configuration for small buckets (merged tiny buckets, skewed inputs): fewer threads, four CTAs per SM
+  static constexpr int SMALL_THREADS = 256;
+  static constexpr int SMALL_IPT = 6;
+  static constexpr int SMALL_CAP = SMALL_THREADS * SMALL_IPT;
 };
 
 // Persistent-grid size of a kernel: resident CTAs per SM x SMs (queried once per instantiation).
@@ -80,17 +84,19 @@ inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cud
   return cudaGetLastError();
 }
 
-template <typename K, int VB, int ALGO, bool STABLE>
+template <typename K, int VB, int ALGO, bool STABLE, bool SMALL = false>
 inline cudaError_t launch_local(const LocalArgs& a, uint32_t items_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
-  auto kernel = local_sort_kernel<K, VB, C::LOCAL_THREADS, C::LOCAL_IPT, ALGO, STABLE>;
-  constexpr size_t smem = sizeof(LocalSmem<K, VB, C::LOCAL_THREADS, C::LOCAL_IPT, ALGO>);
+  constexpr int THREADS = SMALL ? C::SMALL_THREADS : C::LOCAL_THREADS;
+  constexpr int IPT = SMALL ? C::SMALL_IPT : C::LOCAL_IPT;
+  auto kernel = local_sort_kernel<K, VB, THREADS, IPT, ALGO, STABLE>;
+  constexpr size_t smem = sizeof(LocalSmem<K, VB, THREADS, IPT, ALGO>);
   static_assert(smem <= 227 * 1024, "local sort exceeds the 227 KB shared-memory limit");
   static int grid = 0;
-  if (!grid) B200_CHECK(persistent_grid(kernel, C::LOCAL_THREADS, smem, &grid));
+  if (!grid) B200_CHECK(persistent_grid(kernel, THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
-  ProfScope prof(ALGO == ALGO_LSD ? "local_sort_lsd" : "local_sort_count", s);
-  kernel<<<g, C::LOCAL_THREADS, smem, s>>>(a);
+  ProfScope prof(ALGO == ALGO_LSD ? (SMALL ? "local_sort_lsd_small" : "local_sort_lsd") : "local_sort_count", s);
+  kernel<<<g, THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -131,7 +137,7 @@ struct Carver {      // sub-allocates the caller's temporary storage, 256-byte a
 // ===============================================================================================================
 struct MsdWorkspace {
   MsbCounters* ctr; Seg* segs0; Seg* segs1; uint32_t* tile_base; TileDesc* descs; uint32_t* seg_hist; uint64_t* bins;
-  uint32_t* tile_off; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[3];   // LSD list, counting list, overflow
+  uint32_t* tile_off; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[4];   // LSD list, counting list, overflow, small-bucket LSD list
   uint32_t max_segs, max_tiles, max_locals, max_groups;
 };
 
@@ -154,7 +160,7 @@ inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
   w.group_tail = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
   w.group_flag = cv.take<uint32_t>(w.max_groups);
   w.carry = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
-  for (int i = 0; i < 3; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
+  for (int i = 0; i < 4; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
 }
 
 // Pinned 16-byte landing zone for the key-range probe (one per host thread).
@@ -266,6 +272,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     int list = (shift - begin_bit > 16) ? ALGO_COUNT : ALGO_LSD;     // buckets of this level: which on-chip algorithm
     { static const char* e = getenv("B200SORT_LOCAL"); if (e) list = (e[0] == 'c') ? ALGO_COUNT : ALGO_LSD; }
     ca.locals = w.locals[list]; ca.num_locals_ptr = &ctr->num_locals[list]; ca.max_locals = w.max_locals;
+    if (list == ALGO_LSD) { ca.locals_small = w.locals[3]; ca.num_small_ptr = &ctr->num_locals[2]; ca.small_cap = C::SMALL_CAP; }
     ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
     ca.local_cap = C::LOCAL_CAP; ca.merge_cap = C::MERGE_CAP;
     ca.out_buf = (uint32_t)ob;
@@ -289,6 +296,8 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
   la.tw_in = 0;
   B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
+  la.items = w.locals[3]; la.num_items_ptr = &ctr->num_locals[2];          // small buckets: the 256-thread configuration
+  B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true>(la, w.max_locals, s)));
   if (end_bit - begin_bit > 24) {          // some level left more than 16 bits to its buckets
     la.items = w.locals[ALGO_COUNT]; la.num_items_ptr = &ctr->num_locals[ALGO_COUNT];
     B200_CHECK((launch_local<K, VB, ALGO_COUNT, ORDERED>(la, w.max_locals, s)));

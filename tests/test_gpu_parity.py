@@ -399,3 +399,26 @@ def test_full_cfg4_2p29_u64_skewed_msb(gs, dist, param):
 
 def test_full_cfg4_2p29_u64_lsb(gs):
     _full_size(gs, "lsb", 29, 64, 0, "zipf_hash")
+
+
+def test_dist_sorter_single_rank(gs, oracle, tmp_path):
+    """gpu_sort_b200.dist.DistSorter with a one-rank process group: histogram, splitter choice, range partition, local sort with
+    the key-range bit hint -- the whole multi-GPU code path except the peer-memory stores (bench.py --gpus N checks those)."""
+    import torch.distributed as dist
+    from gpu_sort_b200 import dist as gd
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        for pairs, n in ((True, (1 << 20) + 77), (False, 3_000_001)):
+            k = raw_keys(oracle, n, "u32", seed=13, dist="entropy", param=1)
+            v = iota(n, 4) if pairs else None
+            sorter = gd.DistSorter(n, torch.int32, torch.int32 if pairs else None, key_type=KT_ID["u32"])
+            sk, sv, info = sorter.sort(dev(k), dev(v))
+            torch.cuda.synchronize()
+            assert info["count"] == n
+            ek, ev = oracle.lsb_sort(k, v, key_type="u32")
+            assert same_bits(host(sk, k.dtype), ek)
+            if pairs:
+                assert np.array_equal(host(sv, v.dtype), ev)        # stable end to end
+    finally:
+        dist.destroy_process_group()
