@@ -422,3 +422,38 @@ def test_dist_sorter_single_rank(gs, oracle, tmp_path):
                 assert np.array_equal(host(sv, v.dtype), ev)        # stable end to end
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kt,vb", [("u32", 0), ("u32", 4), ("u64", 0), ("u64", 8), ("i32", 4), ("f32", 0)])
+def test_key_range_probe_paths(gs, oracle, kt, vb):
+    """n >= 2^22 switches the key-range probe on: leading bits that are equal in all keys are skipped and the result buffer
+    follows the number of levels actually run.  Small-range keys, an all-equal array, and full-range keys, through both entry
+    points (overwriting and pointer overloads)."""
+    n = (1 << 22) + 3
+    bits = 32 if kt.endswith("32") else 64
+    base = oracle.gen_keys(n, bits, seed=21)
+    variants = {
+        "small_range": base & np.array((1 << 19) - 1, dtype=base.dtype),
+        "high_bits_fixed": (base & np.array((1 << 27) - 1, dtype=base.dtype)) | np.array(0x5 << (bits - 4), dtype=base.dtype),
+        "all_equal": np.full(n, 0x1234567, dtype=base.dtype),
+        "full_range": base,
+    }
+    for name, ku in variants.items():
+        if kt == "f32" and name != "full_range":
+            ku = ku | np.array(0x3F000000, dtype=ku.dtype)       # keep the patterns ordinary positive floats
+        k = ku.view(NP_OF[kt])
+        v = iota(n, vb)
+        ek, ev = oracle.lsb_sort(k, v, key_type=kt)
+        for overwrite in (True, False):
+            rk, rv = run_lsb(gs, k, v, kt, overwrite=overwrite)
+            assert same_bits(rk, ek), (name, overwrite)
+            if vb:
+                assert np.array_equal(rv, ev), (name, overwrite)
+        k0, k1 = dev(k), torch.empty_like(dev(k))
+        v0 = dev(v); v1 = torch.empty_like(v0) if vb else None
+        r = gs.rdxsrt_unstable_sort(k0, v0, n, k1, v1, key_type=KT_ID[kt])
+        torch.cuda.synchronize()
+        assert same_bits(host(r.sorted_keys, k.dtype), ek), name
+        if vb:
+            rv = host(r.sorted_values, v.dtype)
+            assert same_bits(k[rv.astype(np.int64)], ek), name
