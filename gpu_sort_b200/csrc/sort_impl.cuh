@@ -39,6 +39,9 @@ struct Cfg {
 #ifndef B200_LOCAL_IPT32
 #define B200_LOCAL_IPT32 12
 #endif
+#ifndef B200_LOCAL_THREADS32
+#define B200_LOCAL_THREADS32 384
+#endif
   static constexpr int THREADS = B200_SCATTER_THREADS;
   static constexpr int IPT = (sizeof(K) == 4 ? (VB == 0 ? 16 : VB == 4 ? 8 : 5) : (VB == 0 ? 8 : VB == 4 ? 5 : 4)) * B200_IPT_NUM / B200_IPT_DEN;
 #ifndef B200_SCATTER_OCC
@@ -47,7 +50,7 @@ struct Cfg {
   static constexpr int OCC = B200_SCATTER_OCC;        // scatter CTAs per SM the launch bounds ask for
   static constexpr int TILE = THREADS * IPT;
   // local sort: capacity = the largest bucket that is finished on chip (everything larger gets another level)
-  static constexpr int LOCAL_THREADS = sizeof(K) == 4 ? 384 : (VB == 0 ? 768 : 512);
+  static constexpr int LOCAL_THREADS = sizeof(K) == 4 ? B200_LOCAL_THREADS32 : (VB == 0 ? 768 : 512);
   static constexpr int LOCAL_IPT = sizeof(K) == 4 ? (VB == 8 ? 8 : B200_LOCAL_IPT32) : (VB == 0 ? 12 : 8);
   static constexpr int LOCAL_CAP = LOCAL_THREADS * LOCAL_IPT;
   static constexpr uint32_t MERGE_CAP = LOCAL_CAP / 4;  // runs of tiny neighbouring buckets are merged up to this size
