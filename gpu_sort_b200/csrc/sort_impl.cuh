@@ -53,7 +53,10 @@ struct Cfg {
   static constexpr int LOCAL_THREADS = sizeof(K) == 4 ? B200_LOCAL_THREADS32 : (VB == 0 ? 768 : 512);
   static constexpr int LOCAL_IPT = sizeof(K) == 4 ? (VB == 8 ? 8 : B200_LOCAL_IPT32) : (VB == 0 ? 12 : 8);
   static constexpr int LOCAL_CAP = LOCAL_THREADS * LOCAL_IPT;
-  static constexpr uint32_t MERGE_CAP = LOCAL_CAP / 4;  // runs of tiny neighbouring buckets are merged up to this size
+  // runs of small neighbouring buckets are merged into one on-chip item (which then also sorts the current digit): up to the
+  // full capacity where the LSD kernel finishes them (one more 8-bit pass beats many half-empty items), up to a quarter of it
+  // where the one-shot counting sort does (its cells are indexed by the leading bits, which a merged run barely varies)
+  static constexpr uint32_t MERGE_CAP = LOCAL_CAP / 4;
   // second on-chip configuration for small buckets (merged tiny buckets, skewed inputs): fewer threads, four CTAs per SM
   static constexpr int SMALL_THREADS = 256;
   static constexpr int SMALL_IPT = 6;
@@ -277,7 +280,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     ca.locals = w.locals[list]; ca.num_locals_ptr = &ctr->num_locals[list]; ca.max_locals = w.max_locals;
     if (list == ALGO_LSD) { ca.locals_small = w.locals[3]; ca.num_small_ptr = &ctr->num_locals[2]; ca.small_cap = C::SMALL_CAP; }
     ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
-    ca.local_cap = C::LOCAL_CAP; ca.merge_cap = C::MERGE_CAP;
+    ca.local_cap = C::LOCAL_CAP; ca.merge_cap = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP : C::MERGE_CAP;
     ca.out_buf = (uint32_t)ob;
     const int cgrid = (int)std::min<uint32_t>((w.max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
     { ProfScope prof("msb_sched", s); classify_kernel<<<L == 0 ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca); }
@@ -373,7 +376,9 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     // two buffers: the last possible level lands in buffer (passes & 1), so that is where everything is finished
     // (DoubleBuffer semantics: the selector says where); pointer overloads always deliver into the alternate buffers
     int fin = 1;
-    const cudaError_t e = msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s);
+    // keys-only: equal keys are indistinguishable, so the cheaper unstable engine returns the identical result
+    const cudaError_t e = VB == 0 ? msd_sort_run<K, VB, false>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s)
+                                  : msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s);
     if (selector) *selector = fin;
     return e;
   }

@@ -27,3 +27,19 @@ for pairs, desc in ((True, False), (False, True), (False, False)):
     r = dk.Current()
     ok = bool((r[1:] >= r[:-1]).all().item()) if not desc else bool((r[1:] <= r[:-1]).all().item())
     print(json.dumps({"pairs": pairs, "descending": desc, "ms": [round(t, 3) for t in ts], "sorted": ok, "kernels": {k: (c, round(v, 3)) for k, (c, v) in rep.items()}}))
+
+# the reference driver's own functions on the same data (oracle/_ref/libref_lsb.so = lsb/sort.cu compiled unmodified against toolkit CUB 2.8.2)
+import ctypes
+so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_lsb.so")
+if os.path.exists(so):
+    lib = ctypes.CDLL(so)
+    lib.ref_lsb_sortPairsGPU.restype = ctypes.c_float; lib.ref_lsb_sortKeysGPU.restype = ctypes.c_float
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    k0, k1 = torch.empty_like(src), torch.empty_like(src); v0, v1 = torch.empty_like(vsrc), torch.empty_like(vsrc)
+    kv, kk = [], []
+    for it in range(5):
+        k0.copy_(src); v0.copy_(vsrc); torch.cuda.synchronize()
+        kv.append(lib.ref_lsb_sortPairsGPU(P(k0), P(k1), P(v0), P(v1), ctypes.c_int(n)))
+        k0.copy_(src); torch.cuda.synchronize()
+        kk.append(lib.ref_lsb_sortKeysGPU(P(k0), P(k1), ctypes.c_int(n)))
+    print(json.dumps({"reference_lsb_driver_cub_2.8.2": {"time_sort_kv_gpu_ms": [round(x, 3) for x in kv], "time_sort_k_gpu_ms (SortKeysDescending)": [round(x, 3) for x in kk]}}))
