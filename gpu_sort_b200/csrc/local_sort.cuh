@@ -36,16 +36,20 @@ struct LocalArgs {
   Twiddle tw;
 };
 
-constexpr int COUNT_MAX_BITS = 13;       // up to 8192 cells: about one key per cell for the largest bucket a CTA takes
+constexpr int COUNT_MAX_BITS = 16;       // cells when <= 16 bits remain: one cell per remaining key value (no in-cell ordering needed)
+constexpr int COUNT_FIT_BITS = 13;       // cells when more bits remain: ~log2(count), at most 8192 (about one key per cell)
 
-template <int THREADS>
+// MAXBITS = 16 only where the exact-cell mode is used (4-byte keys-only buckets with <= 16 bits left): 48 KB of counters; every
+// other instantiation keeps the compact 13-bit table (6 KB), which leaves the L1 / shared-memory split alone.
+template <int THREADS, int MAXBITS>
 struct CountSmem {
-  static constexpr int WORDS = (1 << COUNT_MAX_BITS) / 8;
-  static_assert(WORDS / 4 <= THREADS, "one 4-word group per thread in the prefix scan");
+  static constexpr int WORDS = (1 << MAXBITS) / 8;
+  static constexpr int NSEG = (WORDS / 4 + THREADS - 1) / THREADS;   // consecutive 4-word groups a thread owns in the prefix scan
   alignas(16) uint32_t nib[WORDS];     // 8 counters of 4 bits per word
   alignas(16) uint16_t wpre[WORDS];    // number of keys in all earlier words
   uint32_t wt[32];                     // per-warp totals of the scan
 };
+template <typename K, int VB> struct CountBits { static constexpr int value = (sizeof(K) == 4 && VB == 0) ? COUNT_MAX_BITS : COUNT_FIT_BITS; };
 
 template <int THREADS>
 struct LsdSmem {
@@ -66,7 +70,7 @@ struct LocalSmem {
   alignas(16) K stage[2][CAP + SLACK];
   alignas(16) V vstage[VB ? 2 : 1][VB ? CAP + VSLACK : 1];
   alignas(16) uint16_t origin[ALGO == ALGO_COUNT ? CAP : 8];    // stable counting sort: input index of the key at each position
-  typename std::conditional<ALGO == ALGO_LSD, LsdSmem<THREADS>, CountSmem<THREADS>>::type rank;
+  typename std::conditional<ALGO == ALGO_LSD, LsdSmem<THREADS>, CountSmem<THREADS, CountBits<K, VB>::value>>::type rank;
   alignas(8) uint64_t bar[2];
   LocalItem item[2];
   uint32_t skew[2], vskew[2];
@@ -79,20 +83,22 @@ struct LocalSmem {
 template <typename K, int VB, int THREADS, int ROWS, bool STABLE>
 __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename ValType<VB>::type* __restrict__ sv, uint16_t* __restrict__ origin,
                                                 uint32_t skew, uint32_t vskew, uint32_t cnt, int lo, int hi, bool tw_in, const Twiddle& tw,
-                                                CountSmem<THREADS>& cs) {
+                                                CountSmem<THREADS, CountBits<K, VB>::value>& cs) {
   using V = typename ValType<VB>::type;
   constexpr int NWARPS = THREADS / 32;
   const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
   const int rows = (int)((cnt + THREADS - 1) / THREADS);
+  constexpr int MAXBITS = CountBits<K, VB>::value;
+  constexpr int NSEG = CountSmem<THREADS, MAXBITS>::NSEG;
   int cbits = 32 - __clz(cnt);
-  cbits = cbits < 6 ? 6 : (cbits > COUNT_MAX_BITS ? COUNT_MAX_BITS : cbits);
-  if (cbits > hi - lo) cbits = hi - lo;
+  cbits = cbits < 6 ? 6 : (cbits > COUNT_FIT_BITS ? COUNT_FIT_BITS : cbits);
+  if (hi - lo <= MAXBITS) cbits = hi - lo;                 // few bits left: one cell per key value
   const int vshift = hi - cbits;
   const uint32_t vmask = (1u << cbits) - 1u;
   const uint32_t words = cbits > 5 ? 1u << (cbits - 3) : 4u;
   const uint32_t groups = words / 4;
 
-  if (tid < groups) reinterpret_cast<uint4*>(cs.nib)[tid] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid; i < groups; i += THREADS) reinterpret_cast<uint4*>(cs.nib)[i] = make_uint4(0, 0, 0, 0);
   K key[ROWS]; uint32_t pos[ROWS]; V val[VB ? ROWS : 1];
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) {
@@ -118,15 +124,18 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
     }
   if (__syncthreads_or(ovf)) return false;
 
-  // ---- exclusive prefix over the counter words; thread t owns the 4-word group t
+  // ---- exclusive prefix over the counter words; thread t owns the NSEG consecutive 4-word groups t*NSEG ..
   {
+    // per-word nibble sums (a word holds <= 8 * 15 keys; a 4-word group can exceed 255, so the words are summed separately)
+    auto wsum = [](uint32_t x) { const uint32_t t = (x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu); return (t * 0x01010101u) >> 24; };
     uint32_t tsum = 0;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (tid < groups) {
-      q = reinterpret_cast<const uint4*>(cs.nib)[tid];
-      // per-word nibble sums (a word holds <= 8 * 15 keys; a 4-word group can exceed 255, so the words are summed separately)
-      auto wsum = [](uint32_t x) { const uint32_t t = (x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu); return (t * 0x01010101u) >> 24; };
-      tsum = wsum(q.x) + wsum(q.y) + wsum(q.z) + wsum(q.w);
+#pragma unroll
+    for (int g = 0; g < NSEG; ++g) {
+      const uint32_t gi = tid * NSEG + g;
+      if (gi < groups) {
+        const uint4 q = reinterpret_cast<const uint4*>(cs.nib)[gi];
+        tsum += wsum(q.x) + wsum(q.y) + wsum(q.z) + wsum(q.w);
+      }
     }
     uint32_t inc = tsum;
 #pragma unroll
@@ -144,16 +153,17 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
       if (lane >= (unsigned)o) wi += t;
     }
     uint32_t run = __shfl_sync(0xffffffffu, wi - wv, w) + inc - tsum;
-    if (tid < groups) {
-      const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-      uint32_t p[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        p[e] = run;
-        const uint32_t t = (qq[e] & 0x0F0F0F0Fu) + ((qq[e] >> 4) & 0x0F0F0F0Fu);
-        run += (t * 0x01010101u) >> 24;
+    for (int g = 0; g < NSEG; ++g) {
+      const uint32_t gi = tid * NSEG + g;
+      if (gi < groups) {
+        const uint4 q = reinterpret_cast<const uint4*>(cs.nib)[gi];
+        const uint32_t p0 = run; run += wsum(q.x);
+        const uint32_t p1 = run; run += wsum(q.y);
+        const uint32_t p2 = run; run += wsum(q.z);
+        const uint32_t p3 = run; run += wsum(q.w);
+        reinterpret_cast<uint2*>(cs.wpre)[gi] = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
       }
-      reinterpret_cast<uint2*>(cs.wpre)[tid] = make_uint2(p[0] | (p[1] << 16), p[2] | (p[3] << 16));
     }
   }
   __syncthreads();
@@ -365,7 +375,7 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
 #define B200_LOCAL_OCC384 2
 #endif
 template <typename K, int VB, int THREADS, int IPT, int ALGO, bool STABLE>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 ? (VB == 0 ? 3 : B200_LOCAL_OCC384) : (sizeof(LocalSmem<K, VB, THREADS, IPT, ALGO>) <= 113 * 1024 && THREADS <= 768) ? 2 : 1)) local_sort_kernel(const __grid_constant__ LocalArgs a) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 ? ((VB == 0 && ALGO == ALGO_LSD) ? 3 : B200_LOCAL_OCC384) : (sizeof(LocalSmem<K, VB, THREADS, IPT, ALGO>) <= 113 * 1024 && THREADS <= 768) ? 2 : 1)) local_sort_kernel(const __grid_constant__ LocalArgs a) {
   using V = typename ValType<VB>::type;
   using SM = LocalSmem<K, VB, THREADS, IPT, ALGO>;
   constexpr unsigned PRODUCER = THREADS - 1;
@@ -435,7 +445,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 
     bool sorted = true;
     if (ALGO == ALGO_COUNT) {
       sorted = count_sort_item<K, VB, THREADS, IPT, STABLE>(sk, sv, sm.origin, skew, vskew, cnt, lo, hi, a.tw_in != 0, a.tw,
-                                                             *reinterpret_cast<CountSmem<THREADS>*>(&sm.rank));
+                                                             *reinterpret_cast<CountSmem<THREADS, CountBits<K, VB>::value>*>(&sm.rank));
       if (!sorted && tid == 0) a.overflow[atomicAdd(a.num_overflow_ptr, 1u)] = it;
     } else {
       lsd_sort_item<K, VB, THREADS, IPT, STABLE>(sk, sv, skew, vskew, cnt, lo, hi, a.tw_in != 0, a.tw, *reinterpret_cast<LsdSmem<THREADS>*>(&sm.rank));

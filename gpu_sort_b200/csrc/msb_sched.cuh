@@ -39,6 +39,7 @@ struct ClassifyArgs {
   Seg* next_segs; uint32_t* num_next_ptr; uint32_t max_segs;
   LocalItem* locals; uint32_t* num_locals_ptr; uint32_t max_locals;
   LocalItem* locals_small; uint32_t* num_small_ptr; uint32_t small_cap;   // buckets of at most small_cap keys go here (nullptr: none)
+  LocalItem* locals_merged; uint32_t* num_merged_ptr;                    // merged runs larger than small_cap go here (nullptr: to `locals`)
   uint32_t* error;
   int shift;                    // bit position of this level's digit; bits [begin_bit, shift) remain below it
   int nb;                       // width of this level's digit (8, or less on the last level of a bit sub-range)
@@ -79,14 +80,18 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
     __syncwarp();
     if (a.last) continue;             // last digit: every sub-bucket is final after the scatter
     // classify + merge, serial over the 256 digits (lane 0), staged in shared memory
-    uint32_t nloc = 0, nseg = 0, nsml = 0;     // big items fill s_loc[w] from the front, small ones from the back
+    uint32_t nloc = 0, nseg = 0, nsml = 0, nmrg = 0;     // big items fill s_loc[w] from the front, small ones from the back;
+    LocalItem* s_mrg = reinterpret_cast<LocalItem*>(&s_seg[w][0]);   // merged runs share s_seg[w] with the segments, from the back
+    static_assert(sizeof(LocalItem) == sizeof(Seg), "merged items are staged in the segment array");
     if (lane == 0) {
       uint64_t pend_off = 0; uint32_t pend_sum = 0, pend_n = 0;
       auto flush = [&]() {
         if (pend_n) {
           LocalItem it; it.off = pend_off; it.cnt = pend_sum;
           it.nbits = (uint16_t)(pend_n > 1 ? a.shift + a.nb : a.shift); it.src = (uint16_t)a.out_buf;
-          if (a.locals_small != nullptr && it.cnt <= a.small_cap) s_loc[w][RADIX - 1 - nsml++] = it; else s_loc[w][nloc++] = it;
+          if (a.locals_small != nullptr && it.cnt <= a.small_cap) s_loc[w][RADIX - 1 - nsml++] = it;
+          else if (a.locals_merged != nullptr && pend_n > 1) s_mrg[RADIX - 1 - nmrg++] = it;
+          else s_loc[w][nloc++] = it;
           pend_n = 0; pend_sum = 0;
         }
       };
@@ -111,22 +116,27 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
     }
     nloc = __shfl_sync(0xffffffffu, nloc, 0);
     nsml = __shfl_sync(0xffffffffu, nsml, 0);
+    nmrg = __shfl_sync(0xffffffffu, nmrg, 0);
     nseg = __shfl_sync(0xffffffffu, nseg, 0);
     __syncwarp();
-    uint32_t lbase = 0, sbase = 0, mbase = 0;
+    uint32_t lbase = 0, sbase = 0, mbase = 0, gbase = 0;
     if (lane == 0) {
       if (nloc) lbase = atomicAdd(a.num_locals_ptr, nloc);
       if (nsml) mbase = atomicAdd(a.num_small_ptr, nsml);
+      if (nmrg) gbase = atomicAdd(a.num_merged_ptr, nmrg);
       if (nseg) sbase = atomicAdd(a.num_next_ptr, nseg);
     }
     lbase = __shfl_sync(0xffffffffu, lbase, 0);
     mbase = __shfl_sync(0xffffffffu, mbase, 0);
+    gbase = __shfl_sync(0xffffffffu, gbase, 0);
     sbase = __shfl_sync(0xffffffffu, sbase, 0);
     if (lbase + nloc > a.max_locals) { if (lane == 0) atomicOr(a.error, (uint32_t)ERR_LOCAL_OVERFLOW); nloc = 0; }
     if (mbase + nsml > a.max_locals) { if (lane == 0) atomicOr(a.error, (uint32_t)ERR_LOCAL_OVERFLOW); nsml = 0; }
+    if (gbase + nmrg > a.max_locals) { if (lane == 0) atomicOr(a.error, (uint32_t)ERR_LOCAL_OVERFLOW); nmrg = 0; }
     if (sbase + nseg > a.max_segs) { if (lane == 0) atomicOr(a.error, (uint32_t)ERR_SEG_OVERFLOW); nseg = 0; }
     for (uint32_t i = lane; i < nloc; i += 32) a.locals[lbase + i] = s_loc[w][i];
     for (uint32_t i = lane; i < nsml; i += 32) a.locals_small[mbase + i] = s_loc[w][RADIX - 1 - i];
+    for (uint32_t i = lane; i < nmrg; i += 32) a.locals_merged[gbase + i] = s_mrg[RADIX - 1 - i];
     for (uint32_t i = lane; i < nseg; i += 32) a.next_segs[sbase + i] = s_seg[w][i];
     __syncwarp();
   }

@@ -275,10 +275,16 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     ClassifyArgs ca{};
     ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = w.seg_hist; ca.bins = w.bins;
     ca.next_segs = nxt; ca.num_next_ptr = &ctr->num_segs[L + 1]; ca.max_segs = w.max_segs;
-    int list = (shift - begin_bit > 16) ? ALGO_COUNT : ALGO_LSD;     // buckets of this level: which on-chip algorithm
+    // buckets of this level: which on-chip algorithm.  More than 16 bits left -> one-shot counting sort; otherwise the unstable
+    // keys-only engine still prefers it for its large unmerged buckets (one cell per key value: half the shared-memory traffic of
+    // two LSD passes); merged runs, small buckets and the stable engine take the LSD kernels
+    int list = (shift - begin_bit > 16) ? ALGO_COUNT : ALGO_LSD;
+    const bool count_big = !ORDERED && VB == 0 && sizeof(K) == 4 && list == ALGO_LSD;
     { static const char* e = getenv("B200SORT_LOCAL"); if (e) list = (e[0] == 'c') ? ALGO_COUNT : ALGO_LSD; }
-    ca.locals = w.locals[list]; ca.num_locals_ptr = &ctr->num_locals[list]; ca.max_locals = w.max_locals;
+    const int big_list = count_big ? ALGO_COUNT : list;
+    ca.locals = w.locals[big_list]; ca.num_locals_ptr = &ctr->num_locals[big_list]; ca.max_locals = w.max_locals;
     if (list == ALGO_LSD) { ca.locals_small = w.locals[3]; ca.num_small_ptr = &ctr->num_locals[2]; ca.small_cap = C::SMALL_CAP; }
+    if (count_big) { ca.locals_merged = w.locals[ALGO_LSD]; ca.num_merged_ptr = &ctr->num_locals[ALGO_LSD]; }   // merged runs need LSD passes
     ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
     ca.local_cap = C::LOCAL_CAP; ca.merge_cap = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP : C::MERGE_CAP;
     ca.out_buf = (uint32_t)ob;
@@ -304,7 +310,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
   la.items = w.locals[3]; la.num_items_ptr = &ctr->num_locals[2];          // small buckets: the 256-thread configuration
   B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true>(la, w.max_locals, s)));
-  if (end_bit - begin_bit > 24) {          // some level left more than 16 bits to its buckets
+  if (end_bit - begin_bit > 24 || (!ORDERED && VB == 0 && sizeof(K) == 4)) {          // some level left more than 16 bits to its buckets / large keys-only buckets
     la.items = w.locals[ALGO_COUNT]; la.num_items_ptr = &ctr->num_locals[ALGO_COUNT];
     B200_CHECK((launch_local<K, VB, ALGO_COUNT, ORDERED>(la, w.max_locals, s)));
     la.items = w.locals[2]; la.num_items_ptr = &ctr->num_overflow;       // buckets with overfull cells: LSD passes instead
