@@ -93,6 +93,7 @@ struct TileHistArgs {
   const void* keys;
   const TileDesc* descs; const uint32_t* num_tiles_ptr;
   uint32_t* tile_off; uint32_t* group_tail; uint32_t* group_flag;
+  uint16_t* tile_cnt;                          // optional: [tile][256] plain counts (for scatter_fast_kernel)
   uint32_t* seg_hist;
   int shift; uint32_t mask; int tw_in; Twiddle tw;
   const uint32_t* splitters; int num_parts;     // range mode: digit = #{ j < num_parts-1 : splitters[j] <= (key >> shift) }
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
           acc = 0; run = 0; flag = 1; cur_seg = td.seg;
         }
         a.tile_off[(uint64_t)t * RADIX + tid] = run;
+        if (a.tile_cnt != nullptr) a.tile_cnt[(uint64_t)t * RADIX + tid] = (uint16_t)c;
         run += c; acc += c;
       }
     }

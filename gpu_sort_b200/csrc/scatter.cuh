@@ -45,6 +45,7 @@ struct ScatterArgs {
                                   // otherwise [256] absolute output index of the start of each digit
   const uint32_t* tile_off;       // MODE_SEG: [tile][256]  keys of the same (segment, digit) in earlier tiles of the tile's group
   const uint32_t* carry;          // MODE_SEG: [group][256] ... and in earlier groups (tile_hist_kernel / group_carry_kernel)
+  const uint16_t* tile_cnt;       // scatter_fast_kernel: [tile][256] keys of every digit in the tile
   uint64_t* bins_next;            // MODE_LSB: the last tile writes bins + portion counts here (or nullptr)
   uint32_t* status;               // MODE_LSB: [tile][256] look-back words, zeroed before the launch
   uint32_t* ticket;               // MODE_LSB: zeroed before the launch
@@ -479,6 +480,215 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_kernel(const __grid_cons
     }
     if (g.cnt == (uint32_t)TILE) scatter_tile<K, VB, THREADS, IPT, MODE, ORD, true>(a, sm, g, slot, num_tiles, it);
     else scatter_tile<K, VB, THREADS, IPT, MODE, ORD, false>(a, sm, g, slot, num_tiles, it);
+    if (tid == PRODUCER) { tk_a = tk_b; td_a = td_b; }
+  }
+}
+
+// ===============================================================================================================
+// scatter_fast_kernel -- the unstable segment scatter (MODE_SEG, atomic ranking) with everything a tile needs from global
+// memory fetched ONE TILE AHEAD by the digit-owner threads: the tile's digit counts (tile_hist_kernel wrote them), their
+// exclusive scan and the global destinations.  The ranking counters start at each digit's first slot, so a key's atomicAdd
+// returns its final position in the reorder buffer directly: no per-key bin_start lookup, no post-rank scan, and two block
+// barriers per tile instead of six (the shared-memory pipe and barrier stalls bound the general kernel, profiles/r01_full_cfg2.txt).
+// ===============================================================================================================
+template <typename K, int VB, int THREADS, int IPT>
+struct FastSmem {
+  static constexpr int TILE = THREADS * IPT;
+  using V = typename ValType<VB>::type;
+  static constexpr int SLACK = 16 / sizeof(K), VSLACK = 16 / sizeof(V);
+  alignas(16) K stage[2][TILE + SLACK];
+  alignas(16) V vstage[VB ? 2 : 1][VB ? TILE + VSLACK : 1];
+  K* kptr[2][RADIX];
+  V* vptr[VB ? 2 : 1][VB ? RADIX : 1];
+  uint32_t cnt[2][RADIX];           // ranking counters, preset to the first slot of every digit
+  uint32_t scratch[2][8];
+  alignas(8) uint64_t bar[2];
+  TileGeom geom[2];
+  uint32_t skewed[2];
+};
+
+template <typename K, int VB, int THREADS, int IPT, int OCC>
+__global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid_constant__ ScatterArgs a) {
+  using SM = FastSmem<K, VB, THREADS, IPT>;
+  using V = typename SM::V;
+  constexpr int TILE = SM::TILE;
+  constexpr unsigned PRODUCER = THREADS - 1;
+  static_assert(THREADS >= 2 * RADIX, "the digit owners (warps 0-7) must not include the producer's warp");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const K* __restrict__ keys_in = reinterpret_cast<const K*>(a.keys_in);
+  const V* __restrict__ vals_in = reinterpret_cast<const V*>(a.vals_in);
+  const uint32_t num_tiles = *a.num_tiles_ptr;
+  const int shift = a.shift; const uint32_t mask = a.mask;
+
+  auto stage_tile = [&](int slot, uint32_t t, const TileDesc& td) {
+    TileGeom g;
+    g.tile = t; g.skew = 0; g.vskew = 0;
+    if (t < num_tiles) {
+      g.off = td.off; g.cnt = td.cnt; g.seg = td.seg; g.tile_in_seg = td.tile_in_seg;
+      const BulkWindow<K> bw(keys_in, g.off, g.cnt);
+      g.skew = bw.skew;
+      uint32_t bytes = bw.bytes;
+      fence_proxy_async();
+      if (VB) {
+        const BulkWindow<V> vw(vals_in, g.off, g.cnt);
+        g.vskew = vw.skew;
+        bytes += vw.bytes;
+        mbar_expect_tx(&sm.bar[slot], bytes);
+        bulk_g2s(&sm.vstage[VB ? slot : 0][0], vw.src, vw.bytes, &sm.bar[slot]);
+      } else {
+        mbar_expect_tx(&sm.bar[slot], bytes);
+      }
+      bulk_g2s(&sm.stage[slot][0], bw.src, bw.bytes, &sm.bar[slot]);
+    } else {
+      g.off = 0; g.cnt = 0; g.seg = 0; g.tile_in_seg = 0;
+    }
+    sm.geom[slot] = g;
+  };
+  // digit owners (threads 0..255): counts, scan and destinations of the tile described by geom[slot] -> cnt / kptr / vptr[slot]
+  auto prepare = [&](int slot) {
+    const TileGeom g = sm.geom[slot];
+    if (g.tile >= num_tiles) return;                       // uniform over the 256 digit owners
+    const uint32_t c = a.tile_cnt[(uint64_t)g.tile * RADIX + tid];
+    const uint32_t grp = g.tile / HIST_GROUP;
+    uint64_t gstart = a.bins[(uint64_t)g.seg * RADIX + tid] + a.tile_off[(uint64_t)g.tile * RADIX + tid];
+    if (g.tile - g.tile_in_seg < grp * HIST_GROUP) gstart += a.carry[(uint64_t)grp * RADIX + tid];     // the segment started in an earlier group
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) sm.scratch[slot][w] = inc;
+    if (tid == 0) sm.skewed[slot] = 0;
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight digit-owner warps only
+    uint32_t woff = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) woff += ((unsigned)j < w) ? sm.scratch[slot][j] : 0u;
+    const uint32_t excl = woff + inc - c;
+    sm.cnt[slot][tid] = excl;
+    sm.kptr[slot][tid] = reinterpret_cast<K*>(a.keys_out) + (gstart - excl);
+    if (VB) sm.vptr[VB ? slot : 0][tid] = reinterpret_cast<V*>(a.vals_out) + (gstart - excl);
+    if (c > (uint32_t)TILE / 4) sm.skewed[slot] = 1;         // dominant digit: aggregate same-digit warps (see scatter_tile)
+  };
+
+  uint32_t tk_a = 0, tk_b = 0;
+  TileDesc td_a{}, td_b{};
+  if (tid == PRODUCER) {
+    mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1);
+    mbar_fence_init();
+    const uint32_t t0 = blockIdx.x;
+    tk_a = t0 + gridDim.x;
+    TileDesc td{};
+    if (t0 < num_tiles) td = a.descs[t0];
+    if (tk_a < num_tiles) td_a = a.descs[tk_a];
+    stage_tile(0, t0, td);
+  }
+  __syncthreads();
+  if (tid < RADIX) prepare(0);
+  __syncthreads();
+
+  for (uint32_t it = 0;; ++it) {
+    const int slot = (int)(it & 1u);
+    const TileGeom g = sm.geom[slot];
+    if (g.tile >= num_tiles) break;
+    const uint32_t cnt = g.cnt;
+    const bool full = cnt == (uint32_t)TILE;
+    if (tid == PRODUCER) {
+      stage_tile(slot ^ 1, tk_a, td_a);          // the other slot is free: its tile finished last iteration
+      tk_b = tk_a + gridDim.x;
+      if (tk_b < num_tiles) td_b = a.descs[tk_b];
+    }
+    K* __restrict__ st = &sm.stage[slot][0];
+    V* __restrict__ vst = &sm.vstage[VB ? slot : 0][0];
+    uint32_t* __restrict__ ctr = sm.cnt[slot];
+
+    // ---- keys: shared memory (TMA-staged) -> registers
+    mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
+    K key[IPT]; uint32_t pos[IPT];
+    {
+      const K* __restrict__ src = st + g.skew + tid;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) key[j] = src[j * THREADS];
+      } else {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) key[j] = (tid + j * THREADS < cnt) ? src[j * THREADS] : (K)~(K)0;
+      }
+    }
+    if (a.tw_in) {
+      const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) key[j] = tw_apply_in<K>(key[j], sg, fl, fp);
+    }
+    // ---- rank: the atomicAdd returns the key's final slot in the reorder buffer
+    if (!sm.skewed[slot]) {
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) pos[j] = atomicAdd(&ctr[digit_of<K>(key[j], shift, mask)], 1u);
+      } else {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j)
+          if (tid + j * THREADS < cnt) pos[j] = atomicAdd(&ctr[digit_of<K>(key[j], shift, mask)], 1u);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        const bool v = tid + j * THREADS < cnt;
+        const unsigned d = digit_of<K>(key[j], shift, mask);
+        const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
+        if (__all_sync(0xffffffffu, v && d == d0)) {
+          unsigned b = 0;
+          if (lane == 0) b = atomicAdd(&ctr[d0], 32u);
+          pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane;
+        } else if (v) {
+          pos[j] = atomicAdd(&ctr[d], 1u);
+        }
+      }
+    }
+    V val[VB ? IPT : 1];
+    if (VB) {
+      const V* __restrict__ vsrc = vst + g.vskew + tid;
+#pragma unroll
+      for (int j = 0; j < IPT; ++j)
+        if (full || tid + j * THREADS < cnt) val[j] = vsrc[j * THREADS];
+    }
+    __syncthreads();          // every thread has its keys (and values) in registers: the staging buffers become the reorder buffers
+#pragma unroll
+    for (int j = 0; j < IPT; ++j)
+      if (full || tid + j * THREADS < cnt) { st[pos[j]] = key[j]; if (VB) vst[pos[j]] = val[j]; }
+    __syncthreads();          // reorder complete; geom[slot ^ 1] (written by the producer above) is visible
+    // ---- digit owners prepare the next tile while everybody writes this one out
+    if (tid < RADIX) prepare(slot ^ 1);
+    // ---- coalesced write-out: consecutive positions of one digit are consecutive output addresses
+    K* const* __restrict__ kp = sm.kptr[slot];
+    V* const* __restrict__ vp = sm.vptr[VB ? slot : 0];
+    if (a.tw_out) {
+      const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        const uint32_t p = j * THREADS + tid;
+        if (full || p < cnt) {
+          const K k = st[p];
+          const uint32_t d = digit_of<K>(k, shift, mask);
+          st_global<K>(kp[d], p, tw_apply_out<K>(k, sg, fl, fp));
+          if (VB) st_global<V>(vp[d], p, vst[p]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        const uint32_t p = j * THREADS + tid;
+        if (full || p < cnt) {
+          const K k = st[p];
+          const uint32_t d = digit_of<K>(k, shift, mask);
+          st_global<K>(kp[d], p, k);
+          if (VB) st_global<V>(vp[d], p, vst[p]);
+        }
+      }
+    }
+    __syncthreads();          // the slot (and cnt / kptr of this slot) may be overwritten from here on
     if (tid == PRODUCER) { tk_a = tk_b; td_a = td_b; }
   }
 }

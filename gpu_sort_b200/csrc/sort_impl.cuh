@@ -76,9 +76,23 @@ inline cudaError_t persistent_grid(KernelT kernel, int threads, size_t smem, int
   return cudaSuccess;
 }
 
+template <typename K, int VB>
+inline cudaError_t launch_scatter_fast(const ScatterArgs& a, uint32_t tiles_hint, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  auto kernel = scatter_fast_kernel<K, VB, C::THREADS, C::IPT, C::OCC>;
+  constexpr size_t smem = sizeof(FastSmem<K, VB, C::THREADS, C::IPT>);
+  static int grid = 0;
+  if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
+  const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
+  ProfScope prof("scatter", s);
+  kernel<<<g, C::THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
 template <typename K, int VB, int MODE, bool ORD>
 inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
+  if (MODE == MODE_SEG && !ORD && C::THREADS >= 2 * RADIX) return launch_scatter_fast<K, VB>(a, tiles_hint, s);
   auto kernel = scatter_kernel<K, VB, C::THREADS, C::IPT, C::OCC, MODE, ORD>;
   constexpr size_t smem = sizeof(ScatterSmem<K, VB, C::THREADS, C::IPT, MODE, ORD>);
   static_assert(smem <= (C::OCC >= 2 ? 113 : 227) * 1024, "the scatter CTAs of one SM must fit its 228 KB of shared memory");
@@ -143,7 +157,7 @@ struct Carver {      // sub-allocates the caller's temporary storage, 256-byte a
 // ===============================================================================================================
 struct MsdWorkspace {
   MsbCounters* ctr; Seg* segs0; Seg* segs1; uint32_t* tile_base; TileDesc* descs; uint32_t* seg_hist; uint64_t* bins;
-  uint32_t* tile_off; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[4];   // LSD list, counting list, overflow, small-bucket LSD list
+  uint32_t* tile_off; uint16_t* tile_cnt; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[4];   // LSD list, counting list, overflow, small-bucket LSD list
   uint32_t max_segs, max_tiles, max_locals, max_groups;
 };
 
@@ -163,6 +177,7 @@ inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
   w.seg_hist = cv.take<uint32_t>((size_t)w.max_segs * RADIX);
   w.bins = cv.take<uint64_t>((size_t)w.max_segs * RADIX);
   w.tile_off = cv.take<uint32_t>((size_t)w.max_tiles * RADIX);
+  w.tile_cnt = cv.take<uint16_t>((size_t)w.max_tiles * RADIX);
   w.group_tail = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
   w.group_flag = cv.take<uint32_t>(w.max_groups);
   w.carry = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
@@ -238,6 +253,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     TileHistArgs ha{};
     ha.keys = bufk[ib]; ha.descs = w.descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
     ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist;
+    ha.tile_cnt = ORDERED ? nullptr : w.tile_cnt;
     ha.shift = shift; ha.mask = mask; ha.tw_in = (L == 0) ? twid : 0; ha.tw = tw;
     ha.key_or = &ctr->key_or; ha.key_and = &ctr->key_and;
     const int hgrid = (int)std::min<uint32_t>(w.max_groups, (uint32_t)sms * 4);
@@ -294,7 +310,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     ScatterArgs pa{};
     pa.keys_in = bufk[ib]; pa.keys_out = bufk[ob]; pa.vals_in = bufv[ib]; pa.vals_out = bufv[ob];
     pa.descs = w.descs; pa.num_tiles_ptr = &ctr->num_tiles[L];
-    pa.bins = w.bins; pa.tile_off = w.tile_off; pa.carry = w.carry;
+    pa.bins = w.bins; pa.tile_off = w.tile_off; pa.carry = w.carry; pa.tile_cnt = w.tile_cnt;
     pa.shift = shift; pa.mask = mask; pa.tw_in = (L == 0) ? twid : 0; pa.tw_out = (shift == begin_bit) ? twid : 0; pa.tw = tw;
     B200_CHECK((launch_scatter<K, VB, MODE_SEG, ORDERED>(pa, w.max_tiles, s)));
 
