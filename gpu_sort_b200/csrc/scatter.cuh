@@ -498,8 +498,7 @@ struct FastSmem {
   static constexpr int SLACK = 16 / sizeof(K), VSLACK = 16 / sizeof(V);
   alignas(16) K stage[2][TILE + SLACK];
   alignas(16) V vstage[VB ? 2 : 1][VB ? TILE + VSLACK : 1];
-  K* kptr[2][RADIX];
-  V* vptr[VB ? 2 : 1][VB ? RADIX : 1];
+  uint32_t goff[2][RADIX];          // per digit: (global start - start inside the tile) mod 2^32; output index = goff[d] + position
   uint32_t cnt[2][RADIX];           // ranking counters, preset to the first slot of every digit
   uint32_t scratch[2][8];
   alignas(8) uint64_t bar[2];
@@ -568,8 +567,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
     for (int j = 0; j < 8; ++j) woff += ((unsigned)j < w) ? sm.scratch[slot][j] : 0u;
     const uint32_t excl = woff + inc - c;
     sm.cnt[slot][tid] = excl;
-    sm.kptr[slot][tid] = reinterpret_cast<K*>(a.keys_out) + (gstart - excl);
-    if (VB) sm.vptr[VB ? slot : 0][tid] = reinterpret_cast<V*>(a.vals_out) + (gstart - excl);
+    sm.goff[slot][tid] = (uint32_t)gstart - excl;          // n < 2^32: indices wrap correctly in 32 bits
     if (c > (uint32_t)TILE / 4) sm.skewed[slot] = 1;         // dominant digit: aggregate same-digit warps (see scatter_tile)
   };
 
@@ -662,8 +660,9 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
     // ---- digit owners prepare the next tile while everybody writes this one out
     if (tid < RADIX) prepare(slot ^ 1);
     // ---- coalesced write-out: consecutive positions of one digit are consecutive output addresses
-    K* const* __restrict__ kp = sm.kptr[slot];
-    V* const* __restrict__ vp = sm.vptr[VB ? slot : 0];
+    const uint32_t* __restrict__ go = sm.goff[slot];
+    K* __restrict__ kout = reinterpret_cast<K*>(a.keys_out);
+    V* __restrict__ vout = reinterpret_cast<V*>(a.vals_out);
     if (a.tw_out) {
       const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
 #pragma unroll
@@ -672,8 +671,9 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
         if (full || p < cnt) {
           const K k = st[p];
           const uint32_t d = digit_of<K>(k, shift, mask);
-          st_global<K>(kp[d], p, tw_apply_out<K>(k, sg, fl, fp));
-          if (VB) st_global<V>(vp[d], p, vst[p]);
+          const uint32_t o = go[d] + p;
+          st_global<K>(kout, o, tw_apply_out<K>(k, sg, fl, fp));
+          if (VB) st_global<V>(vout, o, vst[p]);
         }
       }
     } else {
@@ -683,12 +683,238 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
         if (full || p < cnt) {
           const K k = st[p];
           const uint32_t d = digit_of<K>(k, shift, mask);
-          st_global<K>(kp[d], p, k);
-          if (VB) st_global<V>(vp[d], p, vst[p]);
+          const uint32_t o = go[d] + p;
+          st_global<K>(kout, o, k);
+          if (VB) st_global<V>(vout, o, vst[p]);
         }
       }
     }
     __syncthreads();          // the slot (and cnt / kptr of this slot) may be overwritten from here on
+    if (tid == PRODUCER) { tk_a = tk_b; td_a = td_b; }
+  }
+}
+
+// ===============================================================================================================
+// scatter_stable_fast_kernel -- the stable segment scatter (MODE_SEG, match-mask ranking) on the same one-tile-ahead
+// preparation as scatter_fast_kernel: digit starts come from the scan of the tile's known counts (so no post-rank block scan
+// and no padding correction), destinations are already in shared memory when the tile starts, values are read before the
+// first barrier so keys and values are reordered in one phase: four block barriers per tile instead of seven.
+// ===============================================================================================================
+template <typename K, int VB, int THREADS, int IPT>
+struct StableFastSmem {
+  static constexpr int TILE = THREADS * IPT;
+  static constexpr int WARPS = THREADS / 32;
+  using V = typename ValType<VB>::type;
+  static constexpr int SLACK = 16 / sizeof(K), VSLACK = 16 / sizeof(V);
+  alignas(16) K stage[2][TILE + SLACK];
+  alignas(16) V vstage[VB ? 2 : 1][VB ? TILE + VSLACK : 1];
+  uint32_t goff[2][RADIX];          // per digit: (global start - start inside the tile) mod 2^32; output index = goff[d] + position
+  alignas(16) uint32_t match[2][WARPS * RADIX];   // per-warp match masks, two alternating sets (always zero between rows)
+  alignas(16) uint16_t wcnt[WARPS * RADIX];       // per-warp counters, later per-warp start positions; zero at tile start
+  uint32_t excl[2][RADIX];                        // tile-local exclusive start of every digit (scan of the tile's counts)
+  uint32_t scratch[2][8];
+  alignas(8) uint64_t bar[2];
+  TileGeom geom[2];
+};
+
+template <typename K, int VB, int THREADS, int IPT, int OCC>
+__global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const __grid_constant__ ScatterArgs a) {
+  using SM = StableFastSmem<K, VB, THREADS, IPT>;
+  using V = typename SM::V;
+  constexpr int TILE = SM::TILE, WARPS = SM::WARPS;
+  constexpr unsigned PRODUCER = THREADS - 1;
+  static_assert(THREADS >= 2 * RADIX, "the digit owners (warps 0-7) must not include the producer's warp");
+  static_assert(TILE < 65536, "per-warp start positions are 16-bit");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const K* __restrict__ keys_in = reinterpret_cast<const K*>(a.keys_in);
+  const V* __restrict__ vals_in = reinterpret_cast<const V*>(a.vals_in);
+  const uint32_t num_tiles = *a.num_tiles_ptr;
+  const int shift = a.shift; const uint32_t mask = a.mask;
+
+  auto stage_tile = [&](int slot, uint32_t t, const TileDesc& td) {
+    TileGeom g;
+    g.tile = t; g.skew = 0; g.vskew = 0;
+    if (t < num_tiles) {
+      g.off = td.off; g.cnt = td.cnt; g.seg = td.seg; g.tile_in_seg = td.tile_in_seg;
+      const BulkWindow<K> bw(keys_in, g.off, g.cnt);
+      g.skew = bw.skew;
+      uint32_t bytes = bw.bytes;
+      fence_proxy_async();
+      if (VB) {
+        const BulkWindow<V> vw(vals_in, g.off, g.cnt);
+        g.vskew = vw.skew;
+        bytes += vw.bytes;
+        mbar_expect_tx(&sm.bar[slot], bytes);
+        bulk_g2s(&sm.vstage[VB ? slot : 0][0], vw.src, vw.bytes, &sm.bar[slot]);
+      } else {
+        mbar_expect_tx(&sm.bar[slot], bytes);
+      }
+      bulk_g2s(&sm.stage[slot][0], bw.src, bw.bytes, &sm.bar[slot]);
+    } else {
+      g.off = 0; g.cnt = 0; g.seg = 0; g.tile_in_seg = 0;
+    }
+    sm.geom[slot] = g;
+  };
+  auto prepare = [&](int slot) {      // digit owners (threads 0..255)
+    const TileGeom g = sm.geom[slot];
+    if (g.tile >= num_tiles) return;
+    const uint32_t c = a.tile_cnt[(uint64_t)g.tile * RADIX + tid];
+    const uint32_t grp = g.tile / HIST_GROUP;
+    uint64_t gstart = a.bins[(uint64_t)g.seg * RADIX + tid] + a.tile_off[(uint64_t)g.tile * RADIX + tid];
+    if (g.tile - g.tile_in_seg < grp * HIST_GROUP) gstart += a.carry[(uint64_t)grp * RADIX + tid];
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) sm.scratch[slot][w] = inc;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    uint32_t woff = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) woff += ((unsigned)j < w) ? sm.scratch[slot][j] : 0u;
+    const uint32_t excl = woff + inc - c;
+    sm.excl[slot][tid] = excl;
+    sm.goff[slot][tid] = (uint32_t)gstart - excl;          // n < 2^32: indices wrap correctly in 32 bits
+  };
+
+  uint32_t tk_a = 0, tk_b = 0;
+  TileDesc td_a{}, td_b{};
+  if (tid == PRODUCER) {
+    mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1);
+    mbar_fence_init();
+    const uint32_t t0 = blockIdx.x;
+    tk_a = t0 + gridDim.x;
+    TileDesc td{};
+    if (t0 < num_tiles) td = a.descs[t0];
+    if (tk_a < num_tiles) td_a = a.descs[tk_a];
+    stage_tile(0, t0, td);
+  }
+  {
+    uint4* z = reinterpret_cast<uint4*>(sm.match);
+    for (int i = tid; i < 2 * WARPS * RADIX / 4; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    uint4* zc = reinterpret_cast<uint4*>(sm.wcnt);
+    for (int i = tid; i < WARPS * RADIX / 8; i += THREADS) zc[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  if (tid < RADIX) prepare(0);
+  __syncthreads();
+
+  for (uint32_t it = 0;; ++it) {
+    const int slot = (int)(it & 1u);
+    const TileGeom g = sm.geom[slot];
+    if (g.tile >= num_tiles) break;
+    const uint32_t cnt = g.cnt;
+    const bool full = cnt == (uint32_t)TILE;
+    if (tid == PRODUCER) {
+      stage_tile(slot ^ 1, tk_a, td_a);
+      tk_b = tk_a + gridDim.x;
+      if (tk_b < num_tiles) td_b = a.descs[tk_b];
+    }
+    K* __restrict__ st = &sm.stage[slot][0];
+    V* __restrict__ vst = &sm.vstage[VB ? slot : 0][0];
+
+    // ---- keys (and values): shared memory (TMA-staged) -> registers, warp-contiguous layout (row j of warp w = keys w*32*IPT + j*32 ..)
+    mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
+    K key[IPT]; uint32_t pos[IPT]; V val[VB ? IPT : 1];
+    const uint32_t ibase = w * (32u * IPT) + lane;
+    {
+      const K* __restrict__ src = st + g.skew + ibase;
+      const V* __restrict__ vsrc = vst + g.vskew + ibase;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) { key[j] = src[j * 32]; if (VB) val[j] = vsrc[j * 32]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+          const bool v = ibase + j * 32 < cnt;
+          key[j] = v ? src[j * 32] : (K)~(K)0;            // padding keys (all ones) sit last and rank last
+          if (VB && v) val[j] = vsrc[j * 32];
+        }
+      }
+    }
+    if (a.tw_in) {
+      const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+#pragma unroll
+      for (int j = 0; j < IPT; ++j)
+        if (full || ibase + j * 32 < cnt) key[j] = tw_apply_in<K>(key[j], sg, fl, fp);
+    }
+    // ---- stable ranking inside the warp's share (scatter.cuh, scatter_tile)
+    {
+      uint16_t* wc = sm.wcnt + w * RADIX;
+      const unsigned lt = (1u << lane) - 1u, lbit = 1u << lane;
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        uint32_t* wm = sm.match[j & 1] + w * RADIX;
+        const unsigned d = digit_of<K>(key[j], shift, mask);
+        atomicOr(&wm[d], lbit);
+        __syncwarp();
+        const unsigned peers = wm[d];
+        __syncwarp();
+        const unsigned below = __popc(peers & lt);
+        unsigned b = 0;
+        if (below == 0) { b = wc[d]; wc[d] = (uint16_t)(b + __popc(peers)); wm[d] = 0; }
+        b = __shfl_sync(0xffffffffu, b, __ffs(peers) - 1);
+        pos[j] = b + below;
+      }
+    }
+    __syncthreads();          // (1) all per-warp counts are final; every thread holds its keys and values in registers
+    if (tid < RADIX) {        // per-warp start positions: the digit's start (known a tile ahead) + counts of the lower warps
+      uint32_t run = sm.excl[slot][tid];
+#pragma unroll
+      for (int ww = 0; ww < WARPS; ++ww) {
+        const uint32_t c = sm.wcnt[ww * RADIX + tid];
+        sm.wcnt[ww * RADIX + tid] = (uint16_t)run;
+        run += c;
+      }
+    }
+    __syncthreads();          // (2)
+    {
+      const uint16_t* wc = sm.wcnt + w * RADIX;
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        const uint32_t q = pos[j] + wc[digit_of<K>(key[j], shift, mask)];
+        if (full || q < cnt) { st[q] = key[j]; if (VB) vst[q] = val[j]; }      // padding ranks after every real key: q >= cnt
+      }
+    }
+    __syncthreads();          // (3) reorder complete; geom[slot ^ 1] is visible
+    if (tid < RADIX) prepare(slot ^ 1);
+    {                         // the per-warp counters are free again: zero them for the next tile
+      uint4* zc = reinterpret_cast<uint4*>(sm.wcnt);
+      for (int i = tid; i < WARPS * RADIX / 8; i += THREADS) zc[i] = make_uint4(0, 0, 0, 0);
+    }
+    const uint32_t* __restrict__ go = sm.goff[slot];
+    K* __restrict__ kout = reinterpret_cast<K*>(a.keys_out);
+    V* __restrict__ vout = reinterpret_cast<V*>(a.vals_out);
+    if (a.tw_out) {
+      const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        const uint32_t p = j * THREADS + tid;
+        if (full || p < cnt) {
+          const K k = st[p];
+          const uint32_t d = digit_of<K>(k, shift, mask);
+          const uint32_t o = go[d] + p;
+          st_global<K>(kout, o, tw_apply_out<K>(k, sg, fl, fp));
+          if (VB) st_global<V>(vout, o, vst[p]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        const uint32_t p = j * THREADS + tid;
+        if (full || p < cnt) {
+          const K k = st[p];
+          const uint32_t d = digit_of<K>(k, shift, mask);
+          const uint32_t o = go[d] + p;
+          st_global<K>(kout, o, k);
+          if (VB) st_global<V>(vout, o, vst[p]);
+        }
+      }
+    }
+    __syncthreads();          // (4)
     if (tid == PRODUCER) { tk_a = tk_b; td_a = td_b; }
   }
 }

@@ -89,10 +89,25 @@ inline cudaError_t launch_scatter_fast(const ScatterArgs& a, uint32_t tiles_hint
   return cudaGetLastError();
 }
 
+template <typename K, int VB>
+inline cudaError_t launch_scatter_stable_fast(const ScatterArgs& a, uint32_t tiles_hint, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  auto kernel = scatter_stable_fast_kernel<K, VB, C::THREADS, C::IPT, C::OCC>;
+  constexpr size_t smem = sizeof(StableFastSmem<K, VB, C::THREADS, C::IPT>);
+  static_assert(smem <= 113 * 1024, "two stable scatter CTAs must fit one SM");
+  static int grid = 0;
+  if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
+  const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
+  ProfScope prof("scatter_stable", s);
+  kernel<<<g, C::THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
 template <typename K, int VB, int MODE, bool ORD>
 inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
   if (MODE == MODE_SEG && !ORD && C::THREADS >= 2 * RADIX) return launch_scatter_fast<K, VB>(a, tiles_hint, s);
+  if (MODE == MODE_SEG && ORD && C::THREADS >= 2 * RADIX) return launch_scatter_stable_fast<K, VB>(a, tiles_hint, s);
   auto kernel = scatter_kernel<K, VB, C::THREADS, C::IPT, C::OCC, MODE, ORD>;
   constexpr size_t smem = sizeof(ScatterSmem<K, VB, C::THREADS, C::IPT, MODE, ORD>);
   static_assert(smem <= (C::OCC >= 2 ? 113 : 227) * 1024, "the scatter CTAs of one SM must fit its 228 KB of shared memory");
@@ -253,7 +268,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     TileHistArgs ha{};
     ha.keys = bufk[ib]; ha.descs = w.descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
     ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist;
-    ha.tile_cnt = ORDERED ? nullptr : w.tile_cnt;
+    ha.tile_cnt = w.tile_cnt;
     ha.shift = shift; ha.mask = mask; ha.tw_in = (L == 0) ? twid : 0; ha.tw = tw;
     ha.key_or = &ctr->key_or; ha.key_and = &ctr->key_and;
     const int hgrid = (int)std::min<uint32_t>(w.max_groups, (uint32_t)sms * 4);
