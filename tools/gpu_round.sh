@@ -21,11 +21,11 @@ if [ -x oracle/_ref/msb_gtests_on_b200sort ]; then
 fi
 if [ "${1:-}" = "ncu" ]; then
   # bounded captures: tools/one_sort.py runs 2 sorts; the launch list sees both, the full capture only the second sort's
-  # data-moving kernels (skip the first sort's launches of the same families: 4 levels x (hist + scatter) + 3 on-chip = 11)
+  # data-moving kernels (skip the first sort's launches of the same families: 4 levels x (hist + scatter) + 4 on-chip = 12)
   for w in cfg2 cfg3; do
     python tools/one_sort.py $w > gpurun_out/plain_$w.log 2>&1 &&
     ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$w.csv python tools/one_sort.py $w > gpurun_out/ncu_launches_$w.log 2>&1
-    ncu --set full --clock-control none --import-source on -k regex:"scatter_kernel|local_sort_kernel|tile_hist_kernel" -s 11 -c 11 -f -o gpurun_out/prof_$w \
+    ncu --set full --clock-control none --import-source on -k regex:"scatter|local_sort_kernel|tile_hist_kernel" -s 12 -c 12 -f -o gpurun_out/prof_$w \
         python tools/one_sort.py $w > gpurun_out/ncu_full_$w.log 2>&1
   done
 fi

@@ -12,6 +12,8 @@ import re
 def family(name):
     """kernel family as bench.py / b200_prof_report name it, from a (possibly abbreviated) demangled kernel name"""
     args = [x.strip().split(")")[-1] for x in re.sub(r"^[^<]*<", "", name).split(">")[0].split(",")]
+    if "scatter_stable_fast_kernel" in name: return "scatter_stable"
+    if "scatter_fast_kernel" in name: return "scatter"
     if "scatter_kernel" in name and len(args) >= 7:
         mode, ord_ = args[5], args[6]
         return {"0": "scatter_stable" if ord_ in ("1", "true") else "scatter", "1": "scatter_onesweep", "2": "range_partition"}.get(mode, "scatter")
