@@ -54,6 +54,8 @@ def _load():
     lib.b200_error_string.argtypes = [i32]
     lib.b200_lsb_sort.restype = i32
     lib.b200_lsb_sort.argtypes = [vp, P(sz), vp, vp, vp, vp, P(i32), u64, i32, i32, i32, i32, i32, i32, vp]
+    lib.b200_segmented_sort.restype = i32
+    lib.b200_segmented_sort.argtypes = [vp, P(sz), vp, vp, vp, vp, P(i32), u64, ctypes.c_uint32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.b200_msb_sort.restype = i32
     lib.b200_msb_sort.argtypes = [vp, vp, u64, vp, vp, i32, i32, vp, P(sz), vp, P(vp), P(vp)]
     lib.b200_msb_sort_bits.restype = i32
@@ -195,6 +197,66 @@ class DeviceRadixSort:
                            d_keys_out=None):
         return DeviceRadixSort._run(d_temp_storage, d_keys, None, num_items, begin_bit, end_bit, True, stream, key_type,
                                     d_keys_out, None)
+
+
+class DeviceSegmentedRadixSort:
+    """Mirror of cub::DeviceSegmentedRadixSort (lsb/cub/cub/device/device_segmented_radix_sort.cuh:140-844): every segment
+    ``[d_begin_offsets[i], d_end_offsets[i])`` is sorted on its own (stably), all segments in one call.  Offsets are int32 or
+    int64 device tensors; the CSR form passes ``offsets[:-1]`` and ``offsets[1:]``.  Protocol as DeviceRadixSort."""
+
+    @staticmethod
+    def _run(d_temp_storage, d_keys, d_values, num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit, end_bit,
+             descending, stream, key_type, keys_out=None, values_out=None):
+        overwrite = keys_out is None
+        if overwrite:
+            k_cur, k_alt = d_keys.Current(), d_keys.Alternate()
+            v_cur, v_alt = (d_values.Current(), d_values.Alternate()) if d_values is not None else (None, None)
+        else:
+            k_cur, k_alt, v_cur, v_alt = d_keys, keys_out, d_values, values_out
+        kt = key_type_of(k_cur, key_type)
+        vb = _value_bytes(v_cur)
+        if end_bit is None:
+            end_bit = KEY_BYTES[kt] * 8
+        ob = d_begin_offsets.element_size() if d_begin_offsets is not None else 4
+        if d_begin_offsets is not None and (d_end_offsets.element_size() != ob or ob not in (4, 8)):
+            raise ValueError("segment offsets must both be int32 or both int64")
+        nbytes = ctypes.c_size_t(0 if d_temp_storage is None else d_temp_storage.numel() * d_temp_storage.element_size())
+        sel = ctypes.c_int(0)
+        err = lib.b200_segmented_sort(_ptr(d_temp_storage), ctypes.byref(nbytes), _ptr(k_cur), _ptr(k_alt), _ptr(v_cur), _ptr(v_alt),
+                                      ctypes.byref(sel), num_items, num_segments, _ptr(d_begin_offsets), _ptr(d_end_offsets), ob,
+                                      kt, vb, begin_bit, end_bit, int(descending), int(overwrite), _stream(stream))
+        _check(err, "b200_segmented_sort")
+        if d_temp_storage is None:
+            return nbytes.value
+        if overwrite:
+            d_keys.selector ^= sel.value
+            if d_values is not None:
+                d_values.selector ^= sel.value
+        return nbytes.value
+
+    @staticmethod
+    def SortPairs(d_temp_storage, d_keys, d_values, num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit=0,
+                  end_bit=None, stream=None, key_type=None, d_keys_out=None, d_values_out=None):
+        return DeviceSegmentedRadixSort._run(d_temp_storage, d_keys, d_values, num_items, num_segments, d_begin_offsets, d_end_offsets,
+                                             begin_bit, end_bit, False, stream, key_type, d_keys_out, d_values_out)
+
+    @staticmethod
+    def SortPairsDescending(d_temp_storage, d_keys, d_values, num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit=0,
+                            end_bit=None, stream=None, key_type=None, d_keys_out=None, d_values_out=None):
+        return DeviceSegmentedRadixSort._run(d_temp_storage, d_keys, d_values, num_items, num_segments, d_begin_offsets, d_end_offsets,
+                                             begin_bit, end_bit, True, stream, key_type, d_keys_out, d_values_out)
+
+    @staticmethod
+    def SortKeys(d_temp_storage, d_keys, num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit=0, end_bit=None,
+                 stream=None, key_type=None, d_keys_out=None):
+        return DeviceSegmentedRadixSort._run(d_temp_storage, d_keys, None, num_items, num_segments, d_begin_offsets, d_end_offsets,
+                                             begin_bit, end_bit, False, stream, key_type, d_keys_out, None)
+
+    @staticmethod
+    def SortKeysDescending(d_temp_storage, d_keys, num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit=0, end_bit=None,
+                           stream=None, key_type=None, d_keys_out=None):
+        return DeviceSegmentedRadixSort._run(d_temp_storage, d_keys, None, num_items, num_segments, d_begin_offsets, d_end_offsets,
+                                             begin_bit, end_bit, True, stream, key_type, d_keys_out, None)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -175,6 +175,18 @@ int b200_lsb_sort(void* d_temp, size_t* temp_bytes, void* d_keys_current, void* 
                                                     allow_overwrite, s)));
 }
 
+int b200_segmented_sort(void* d_temp, size_t* temp_bytes, void* d_keys_current, void* d_keys_alternate, void* d_values_current,
+                        void* d_values_alternate, int* selector_out, uint64_t num_items, uint32_t num_segments,
+                        const void* d_begin_offsets, const void* d_end_offsets, int offset_bytes, int key_type, int value_bytes,
+                        int begin_bit, int end_bit, int descending, int allow_overwrite, b200_stream_t stream) {
+  Twiddle tw; int kb;
+  if (!make_twiddle(key_type, descending, &tw, &kb) || temp_bytes == nullptr) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_KV(kb, value_bytes, (segmented_sort_impl<K, V>(d_temp, temp_bytes, d_keys_current, d_keys_alternate, d_values_current,
+                                                          d_values_alternate, selector_out, num_items, num_segments, d_begin_offsets,
+                                                          d_end_offsets, offset_bytes, tw, begin_bit, end_bit, allow_overwrite, s)));
+}
+
 int b200_msb_sort_bits(void* d_keys, void* d_values, uint64_t num_items, void* d_keys_alt, void* d_values_alt, int key_type,
                        int value_bytes, int begin_bit, int end_bit, void* d_workspace, size_t* workspace_bytes, b200_stream_t stream,
                        void** out_keys, void** out_values) {

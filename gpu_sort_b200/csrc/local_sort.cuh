@@ -80,10 +80,12 @@ struct LocalSmem {
 // ALGO_COUNT.  Returns false (nothing modified) if a cell overflowed; on success the sorted bucket is at sk[0..cnt),
 // sv[0..cnt).
 // ---------------------------------------------------------------------------------------------------------------
+// Exact-cell keys-only buckets land at sk[aoff .. aoff+cnt) (aoff = the bucket's element offset inside its 16-byte granule of the
+// output), so that the write-out can move aligned 16-byte vectors from shared memory to the output.
 template <typename K, int VB, int THREADS, int ROWS, bool STABLE>
 __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename ValType<VB>::type* __restrict__ sv, uint16_t* __restrict__ origin,
                                                 uint32_t skew, uint32_t vskew, uint32_t cnt, int lo, int hi, bool tw_in, const Twiddle& tw,
-                                                CountSmem<THREADS, CountBits<K, VB>::value>& cs) {
+                                                CountSmem<THREADS, CountBits<K, VB>::value>& cs, uint32_t aoff) {
   using V = typename ValType<VB>::type;
   constexpr int NWARPS = THREADS / 32;
   const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
@@ -183,7 +185,7 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
       const uint32_t c0 = (uint32_t)cs.wpre[v >> 3] + below;
       cell0[j] = c0 | (((wd >> sh) & 15u) << 16);
       pos[j] += c0;
-      sk[pos[j]] = key[j];
+      sk[aoff + pos[j]] = key[j];
       if (STABLE) origin[pos[j]] = (uint16_t)idx;
     }
   }
@@ -374,6 +376,9 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
 #ifndef B200_LOCAL_OCC384
 #define B200_LOCAL_OCC384 2
 #endif
+#ifndef B200_LOCAL_VEC_OUT
+#define B200_LOCAL_VEC_OUT 1
+#endif
 template <typename K, int VB, int THREADS, int IPT, int ALGO, bool STABLE>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 ? ((VB == 0 && ALGO == ALGO_LSD) ? 3 : B200_LOCAL_OCC384) : (sizeof(LocalSmem<K, VB, THREADS, IPT, ALGO>) <= 113 * 1024 && THREADS <= 768) ? 2 : 1)) local_sort_kernel(const __grid_constant__ LocalArgs a) {
   using V = typename ValType<VB>::type;
@@ -443,16 +448,39 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 
     V* __restrict__ sv = &sm.vstage[VB ? slot : 0][0];
 
     bool sorted = true;
+    bool vec = false; uint32_t aoff = 0;
     if (ALGO == ALGO_COUNT) {
+      vec = B200_LOCAL_VEC_OUT && !STABLE && VB == 0 && hi - lo <= CountBits<K, VB>::value;       // exact cells: no in-cell ordering step touches sk
+      aoff = vec ? (uint32_t)((reinterpret_cast<uintptr_t>(keys_out + it.off) & 15u) / sizeof(K)) : 0u;
       sorted = count_sort_item<K, VB, THREADS, IPT, STABLE>(sk, sv, sm.origin, skew, vskew, cnt, lo, hi, a.tw_in != 0, a.tw,
-                                                             *reinterpret_cast<CountSmem<THREADS, CountBits<K, VB>::value>*>(&sm.rank));
+                                                             *reinterpret_cast<CountSmem<THREADS, CountBits<K, VB>::value>*>(&sm.rank), aoff);
       if (!sorted && tid == 0) a.overflow[atomicAdd(a.num_overflow_ptr, 1u)] = it;
     } else {
       lsd_sort_item<K, VB, THREADS, IPT, STABLE>(sk, sv, skew, vskew, cnt, lo, hi, a.tw_in != 0, a.tw, *reinterpret_cast<LsdSmem<THREADS>*>(&sm.rank));
     }
 
     // ---- coalesced write-out of the sorted bucket
-    if (sorted) {
+    if (sorted && vec) {
+      // the bucket sits at sk[aoff ..): shared-memory vector v and output vector v cover the same elements, both 16-byte aligned
+      constexpr uint32_t E = 16 / sizeof(K);
+      K* __restrict__ gdst = keys_out + it.off - aoff;
+      const uint32_t total = aoff + cnt, nvec = (total + E - 1) / E;
+      const bool two = a.tw_out != 0;
+      for (uint32_t v = tid; v < nvec; v += THREADS) {
+        uint4 q = reinterpret_cast<const uint4*>(sk)[v];
+        K* e = reinterpret_cast<K*>(&q);
+        if (two) {
+#pragma unroll
+          for (uint32_t i = 0; i < E; ++i) e[i] = twiddle_out<K>(e[i], a.tw);
+        }
+        if (v * E >= aoff && v * E + E <= total) reinterpret_cast<uint4*>(gdst)[v] = q;
+        else {
+#pragma unroll
+          for (uint32_t i = 0; i < E; ++i)
+            if (v * E + i >= aoff && v * E + i < total) gdst[v * E + i] = e[i];
+        }
+      }
+    } else if (sorted) {
       if (a.tw_out) {
         for (uint32_t pidx = tid; pidx < cnt; pidx += THREADS) {
           keys_out[it.off + pidx] = twiddle_out<K>(sk[pidx], a.tw);

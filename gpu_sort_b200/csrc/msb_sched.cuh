@@ -21,6 +21,7 @@ struct MsbCounters {            // one small zero-initialised block in the works
   uint32_t num_overflow;        // buckets the counting sort handed back
   uint32_t error;
   uint32_t pad;
+  uint32_t num_direct[2];       // segmented sort: caller segments that fit on chip as they are (large / small on-chip configuration)
   unsigned long long key_or, key_and;     // OR / AND of all transformed keys (level-0 histogram): bits where they agree are constant
 };
 
@@ -30,6 +31,46 @@ static __global__ void msb_init_kernel(Seg* segs, MsbCounters* c, uint64_t n) {
     c->num_segs[0] = 1;
     c->key_or = 0ull; c->key_and = ~0ull;
   }
+}
+
+// Segmented sort (cub::DeviceSegmentedRadixSort, lsb/cub/cub/device/device_segmented_radix_sort.cuh:140-760): the caller's
+// segments ARE the level-0 buckets of the MSD engine.  A segment that fits a CTA's shared memory becomes an on-chip work item
+// straight away (its keys are still in caller form: these items get their own launch with the input transform on); a larger
+// one enters the level loop like any bucket.  Empty segments (end <= begin) vanish.  Reference semantics: segments do not
+// overlap; offsets outside [0, n] raise the error flag and the segment is dropped.
+struct SegInitArgs {
+  const void* begin; const void* end; uint32_t num_segments; int offset_bytes;
+  uint64_t n;
+  Seg* segs; uint32_t max_segs;
+  LocalItem* direct; LocalItem* direct_small;
+  MsbCounters* ctr;
+  uint32_t local_cap, small_cap;
+  int end_bit;
+};
+static __global__ void __launch_bounds__(256) seg_init_kernel(const __grid_constant__ SegInitArgs a) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.ctr->key_or = 0ull; a.ctr->key_and = ~0ull; }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.num_segments; i += gridDim.x * blockDim.x) {
+    long long b, e;
+    if (a.offset_bytes == 8) { b = reinterpret_cast<const long long*>(a.begin)[i]; e = reinterpret_cast<const long long*>(a.end)[i]; }
+    else { b = reinterpret_cast<const int*>(a.begin)[i]; e = reinterpret_cast<const int*>(a.end)[i]; }
+    if (e <= b) continue;
+    if (b < 0 || (unsigned long long)e > a.n) { atomicOr(&a.ctr->error, (uint32_t)ERR_SEG_OVERFLOW); continue; }
+    const uint64_t cnt = (uint64_t)(e - b);
+    if (cnt <= a.local_cap) {
+      LocalItem it; it.off = (uint64_t)b; it.cnt = (uint32_t)cnt; it.nbits = (uint16_t)a.end_bit; it.src = 0;
+      if (cnt <= a.small_cap) a.direct_small[atomicAdd(&a.ctr->num_direct[1], 1u)] = it;
+      else a.direct[atomicAdd(&a.ctr->num_direct[0], 1u)] = it;
+    } else {
+      const uint32_t slot = atomicAdd(&a.ctr->num_segs[0], 1u);
+      if (slot >= a.max_segs) { atomicOr(&a.ctr->error, (uint32_t)ERR_SEG_OVERFLOW); continue; }
+      Seg sg; sg.off = (uint64_t)b; sg.cnt = cnt;
+      a.segs[slot] = sg;
+    }
+  }
+}
+
+static __global__ void seg_clamp_kernel(MsbCounters* c, uint32_t max_segs) {
+  if (c->num_segs[0] > max_segs) c->num_segs[0] = 0;      // overlapping segments: the error flag is already up, nothing is sorted
 }
 
 struct ClassifyArgs {

@@ -24,6 +24,11 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
                           uint64_t n, const Twiddle& tw, int begin_bit, int end_bit, int allow_overwrite, cudaStream_t s);
 
 template <typename K, int VB>
+cudaError_t segmented_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, void* v0, void* v1, int* selector,
+                                uint64_t n, uint32_t num_segments, const void* d_begin, const void* d_end, int offset_bytes,
+                                const Twiddle& tw, int begin_bit, int end_bit, int allow_overwrite, cudaStream_t s);
+
+template <typename K, int VB>
 cudaError_t msb_sort_impl(void* keys, void* vals, uint64_t n, void* keys_alt, void* vals_alt, const Twiddle& tw,
                           void* d_ws, size_t* ws_bytes, cudaStream_t s, void** out_keys, void** out_vals, int begin_bit, int end_bit);
 

@@ -207,10 +207,17 @@ inline unsigned long long* probe_buffer() {
 }
 constexpr uint64_t PROBE_MIN_ITEMS = 1ull << 22;     // below this the extra stream synchronisation costs more than it can save
 
+// Caller-defined segments (segmented sort): offsets on the device, plus two work lists for the segments that fit on chip as they are.
+struct SegInput {
+  const void* begin; const void* end; uint32_t num_segments; int offset_bytes;
+  LocalItem* direct; LocalItem* direct_small;
+};
+
 // fin_in: buffer the result must land in (-1: the engine picks bufk[levels & 1] of the two ping-pong buffers); *fin_out says where it is.
+// segin != nullptr: every caller segment is sorted on its own (the segments replace the single level-0 bucket [0, n)).
 template <typename K, int VB, bool ORDERED>
 cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const bufv[3], int nbuf, int fin_in, int* fin_out, uint64_t n,
-                         const Twiddle& tw, int begin_bit, int end_bit, cudaStream_t s) {
+                         const Twiddle& tw, int begin_bit, int end_bit, cudaStream_t s, const SegInput* segin = nullptr) {
   using C = Cfg<K, VB>;
   using V = typename ValType<VB>::type;
   const int sms = num_sms();
@@ -231,7 +238,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   la.overflow = w.locals[2]; la.num_overflow_ptr = &ctr->num_overflow;
   la.tw_out = twid; la.begin_bit = begin_bit; la.tw = tw;
 
-  if (n <= (uint64_t)C::LOCAL_CAP) {     // fits one CTA: a single on-chip sort straight into the final buffer
+  if (segin == nullptr && n <= (uint64_t)C::LOCAL_CAP) {     // fits one CTA: a single on-chip sort straight into the final buffer
     if (fin_in < 0) fin = 0;
     if (fin_out) *fin_out = fin;
     la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
@@ -243,7 +250,17 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
   {
     ProfScope prof("msb_sched", s);
-    msb_init_kernel<<<1, 32, 0, s>>>(w.segs0, ctr, n);
+    if (segin != nullptr) {
+      SegInitArgs sa{};
+      sa.begin = segin->begin; sa.end = segin->end; sa.num_segments = segin->num_segments; sa.offset_bytes = segin->offset_bytes;
+      sa.n = n; sa.segs = w.segs0; sa.max_segs = w.max_segs; sa.direct = segin->direct; sa.direct_small = segin->direct_small;
+      sa.ctr = ctr; sa.local_cap = C::LOCAL_CAP; sa.small_cap = C::SMALL_CAP; sa.end_bit = end_bit;
+      const int sgrid = (int)std::min<uint32_t>((segin->num_segments + 255) / 256, (uint32_t)sms * 8);
+      seg_init_kernel<<<std::max(sgrid, 1), 256, 0, s>>>(sa);
+      seg_clamp_kernel<<<1, 1, 0, s>>>(ctr, w.max_segs);
+    } else {
+      msb_init_kernel<<<1, 32, 0, s>>>(w.segs0, ctr, n);
+    }
     scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(w.segs0, &ctr->num_segs[0], w.tile_base, &ctr->num_tiles[0], w.max_tiles, &ctr->error, C::TILE);
     fill_descs_kernel<<<sms * 2, 256, 0, s>>>(w.segs0, w.tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], w.descs, C::TILE);
   }
@@ -251,7 +268,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   // the order, so the digit windows start below them (small-range keys, e.g. indices below 2^20 in 64-bit keys, would
   // otherwise spend whole sweeps on single-bucket levels).  Costs one 16-byte read-back + stream synchronisation; skipped for
   // small inputs and while the stream is being captured into a CUDA graph.
-  bool probe = n >= PROBE_MIN_ITEMS && levels > 1;
+  bool probe = n >= PROBE_MIN_ITEMS && levels > 1 && segin == nullptr;
   if (probe) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone || probe_buffer() == nullptr) probe = false;
@@ -320,7 +337,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     ca.local_cap = C::LOCAL_CAP; ca.merge_cap = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP : C::MERGE_CAP;
     ca.out_buf = (uint32_t)ob;
     const int cgrid = (int)std::min<uint32_t>((w.max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
-    { ProfScope prof("msb_sched", s); classify_kernel<<<L == 0 ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca); }
+    { ProfScope prof("msb_sched", s); classify_kernel<<<(L == 0 && segin == nullptr) ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca); }
 
     ScatterArgs pa{};
     pa.keys_in = bufk[ib]; pa.keys_out = bufk[ob]; pa.vals_in = bufv[ib]; pa.vals_out = bufv[ob];
@@ -337,6 +354,14 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   }
   if (fin_out) *fin_out = fin;
   la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
+  if (segin != nullptr) {      // segments that fit on chip untouched: still in caller form, all of [begin_bit, end_bit) to sort
+    la.tw_in = twid;
+    la.items = segin->direct; la.num_items_ptr = &ctr->num_direct[0];
+    B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, segin->num_segments, s)));
+    la.items = segin->direct_small; la.num_items_ptr = &ctr->num_direct[1];
+    B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true>(la, segin->num_segments, s)));
+    la.items = w.locals[0]; la.num_items_ptr = &ctr->num_locals[0];
+  }
   la.tw_in = 0;
   B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
   la.items = w.locals[3]; la.num_items_ptr = &ctr->num_locals[2];          // small buckets: the 256-thread configuration
@@ -457,6 +482,57 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
   }
   if (selector) *selector = allow_overwrite ? (passes & 1) : 1;
   return cudaSuccess;
+}
+
+// ===============================================================================================================
+// Segmented stable sort behind the cub::DeviceSegmentedRadixSort call shape (lsb/cub/cub/device/device_segmented_radix_sort.cuh:
+// 140-760; CUB runs one CTA-group per segment, dispatch_radix_sort.cuh:321-436).  Here the segments are simply the level-0
+// buckets of the MSD engine: small segments go straight to the on-chip sorts (thousands per launch), large ones are split by
+// the level loop -- no per-segment launch, no host read-back.  Buffer / selector / temporary-storage conventions as lsb_sort_impl.
+// Elements that belong to no segment are unspecified in the output buffer (as in CUB).
+// ===============================================================================================================
+template <typename K, int VB>
+cudaError_t segmented_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, void* v0, void* v1, int* selector,
+                                uint64_t n, uint32_t num_segments, const void* d_begin, const void* d_end, int offset_bytes,
+                                const Twiddle& tw, int begin_bit, int end_bit, int allow_overwrite, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  using V = typename ValType<VB>::type;
+  constexpr int KEY_BITS = sizeof(K) * 8;
+  if (begin_bit < 0) begin_bit = 0;
+  if (end_bit > KEY_BITS) end_bit = KEY_BITS;
+  if (n >= (1ull << 32) || (offset_bytes != 4 && offset_bytes != 8)) return cudaErrorInvalidValue;
+  const int passes = end_bit > begin_bit ? (end_bit - begin_bit + 7) / 8 : 0;
+  const bool need_third = !allow_overwrite && passes > 1 && n > (uint64_t)C::LOCAL_CAP;
+
+  Carver cv(d_temp);
+  MsdWorkspace w{};
+  msd_carve<K, VB>(cv, n, w);
+  SegInput si{};
+  si.begin = d_begin; si.end = d_end; si.num_segments = num_segments; si.offset_bytes = offset_bytes;
+  si.direct = cv.take<LocalItem>((size_t)num_segments + 1);
+  si.direct_small = cv.take<LocalItem>((size_t)num_segments + 1);
+  K* k2 = need_third ? cv.take<K>(n) : nullptr;
+  V* v2 = (need_third && VB) ? cv.take<V>(n) : nullptr;
+  if (d_temp == nullptr) { *temp_bytes = std::max<size_t>(cv.total(), 256); return cudaSuccess; }
+  if (*temp_bytes < cv.total()) return cudaErrorInvalidValue;
+
+  if (selector) *selector = 0;
+  if (n == 0 || num_segments == 0) return cudaSuccess;
+  if (d_begin == nullptr || d_end == nullptr) return cudaErrorInvalidValue;
+  if (passes == 0) {
+    if (!allow_overwrite) {
+      B200_CHECK(cudaMemcpyAsync(k1, k0, n * sizeof(K), cudaMemcpyDeviceToDevice, s));
+      if (VB) B200_CHECK(cudaMemcpyAsync(v1, v0, n * sizeof(V), cudaMemcpyDeviceToDevice, s));
+      if (selector) *selector = 1;
+    }
+    return cudaSuccess;
+  }
+  void* bufk[3] = {k0, k1, k2}; void* bufv[3] = {v0, v1, v2};
+  int fin = 1;
+  const cudaError_t e = VB == 0 ? msd_sort_run<K, VB, false>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si)
+                                : msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si);
+  if (selector) *selector = fin;
+  return e;
 }
 
 // ===============================================================================================================

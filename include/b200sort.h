@@ -70,6 +70,30 @@ B200_API int b200_lsb_sort(void* d_temp, size_t* temp_bytes,
                   int descending, int allow_overwrite, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Segmented stable radix sort: every segment [d_begin_offsets[i], d_end_offsets[i]) of the key (and value) array is sorted on
+ * its own, in ONE call.
+ * Replaces cub::DeviceSegmentedRadixSort::SortPairs / SortPairsDescending / SortKeys / SortKeysDescending,
+ *   pointer overloads       lsb/cub/cub/device/device_segmented_radix_sort.cuh:140-181, 338-379, 534-572, 716-754
+ *   DoubleBuffer overloads  lsb/cub/cub/device/device_segmented_radix_sort.cuh:247-283, 445-481, 630-666, 808-844
+ * (dispatch: DeviceSegmentedRadixSortKernel, lsb/cub/cub/device/dispatch/dispatch_radix_sort.cuh:321-436).
+ *
+ *   num_segments / d_*_offsets : offsets live on the device; offset_bytes = 4 (CUB's `const int*`) or 8.  A segment with
+ *                                end <= begin is empty.  The usual CSR form passes d_offsets and d_offsets + 1.
+ *                                Segments must not overlap.  Elements outside every segment are unspecified in the
+ *                                result buffer, as in CUB.
+ *   everything else            : as b200_lsb_sort (two-phase temporary storage, selector_out, [begin_bit,end_bit), descending,
+ *                                allow_overwrite).  num_items = length of the key array (< 2^32).
+ * Stable inside every segment.
+ * ------------------------------------------------------------------------------------------------------------------ */
+B200_API int b200_segmented_sort(void* d_temp, size_t* temp_bytes,
+                        void* d_keys_current, void* d_keys_alternate,
+                        void* d_values_current, void* d_values_alternate,
+                        int* selector_out, uint64_t num_items, uint32_t num_segments,
+                        const void* d_begin_offsets, const void* d_end_offsets, int offset_bytes,
+                        int key_type, int value_bytes, int begin_bit, int end_bit,
+                        int descending, int allow_overwrite, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Unstable MSB hybrid radix sort.
  * Replaces rdxsrt_unstable_sort<KeyT,ValueT,IndexT>(dev_keys, dev_values|NULL, key_count, dev_sorted_keys_out,
  *   dev_sorted_values_out|NULL, cfg, pre_allocated_dm, stream)         msb/src/sort/gpu_radix_sort.h:187-507

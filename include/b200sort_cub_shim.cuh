@@ -76,4 +76,63 @@ struct B200DeviceRadixSort {
   B200_CUB_ENTRY(Sort, Descending)
 #undef B200_CUB_ENTRY
 };
+
+// cub::DeviceSegmentedRadixSort call shape (lsb/cub/cub/device/device_segmented_radix_sort.cuh:140-181,247-283,338-379,
+// 445-481,534-572,630-666,716-754,808-844) on b200_segmented_sort: `const int*` segment offsets, otherwise as above.
+struct B200DeviceSegmentedRadixSort {
+  template <typename KeyT, typename ValueT>
+  static cudaError_t run(void* d_temp, size_t& bytes, KeyT* k_cur, KeyT* k_alt, ValueT* v_cur, ValueT* v_alt, int* selector, int n, int num_segments,
+                         const int* d_begin_offsets, const int* d_end_offsets, int begin_bit, int end_bit, bool descending, bool overwrite,
+                         cudaStream_t stream, bool debug_synchronous) {
+    const int e = b200_segmented_sort(d_temp, &bytes, k_cur, k_alt, v_cur, v_alt, selector, (uint64_t)n, (uint32_t)num_segments, d_begin_offsets,
+                                      d_end_offsets, 4, b200detail::kt<KeyT>::v, std::is_same<ValueT, NullType>::value ? 0 : (int)sizeof(ValueT),
+                                      begin_bit, end_bit, descending ? 1 : 0, overwrite ? 1 : 0, (b200_stream_t)stream);
+    if (e == 0 && debug_synchronous && d_temp) return cudaStreamSynchronize(stream);
+    return (cudaError_t)e;
+  }
+#define B200_CUB_SEG_ENTRY(DESC)                                                                                                            \
+  template <typename KeyT, typename ValueT>                                                                                                 \
+  static cudaError_t SortPairs##DESC(void* d_temp_storage, size_t& temp_storage_bytes, DoubleBuffer<KeyT>& d_keys, DoubleBuffer<ValueT>& d_values, \
+                                     int num_items, int num_segments, const int* d_begin_offsets, const int* d_end_offsets, int begin_bit = 0, \
+                                     int end_bit = sizeof(KeyT) * 8, cudaStream_t stream = 0, bool debug_synchronous = false) {             \
+    int sel = 0;                                                                                                                            \
+    cudaError_t e = run<KeyT, ValueT>(d_temp_storage, temp_storage_bytes, d_keys.Current(), d_keys.Alternate(), d_values.Current(),         \
+                                      d_values.Alternate(), &sel, num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit, end_bit, \
+                                      sizeof(#DESC) > 1, true, stream, debug_synchronous);                                                  \
+    if (d_temp_storage && e == cudaSuccess) { d_keys.selector ^= sel; d_values.selector ^= sel; }                                           \
+    return e;                                                                                                                               \
+  }                                                                                                                                         \
+  template <typename KeyT, typename ValueT>                                                                                                 \
+  static cudaError_t SortPairs##DESC(void* d_temp_storage, size_t& temp_storage_bytes, const KeyT* d_keys_in, KeyT* d_keys_out,             \
+                                     const ValueT* d_values_in, ValueT* d_values_out, int num_items, int num_segments,                      \
+                                     const int* d_begin_offsets, const int* d_end_offsets, int begin_bit = 0, int end_bit = sizeof(KeyT) * 8, \
+                                     cudaStream_t stream = 0, bool debug_synchronous = false) {                                             \
+    return run<KeyT, ValueT>(d_temp_storage, temp_storage_bytes, const_cast<KeyT*>(d_keys_in), d_keys_out, const_cast<ValueT*>(d_values_in), \
+                             d_values_out, nullptr, num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit, end_bit,            \
+                             sizeof(#DESC) > 1, false, stream, debug_synchronous);                                                          \
+  }                                                                                                                                         \
+  template <typename KeyT>                                                                                                                  \
+  static cudaError_t SortKeys##DESC(void* d_temp_storage, size_t& temp_storage_bytes, DoubleBuffer<KeyT>& d_keys, int num_items,            \
+                                    int num_segments, const int* d_begin_offsets, const int* d_end_offsets, int begin_bit = 0,              \
+                                    int end_bit = sizeof(KeyT) * 8, cudaStream_t stream = 0, bool debug_synchronous = false) {              \
+    int sel = 0;                                                                                                                            \
+    cudaError_t e = run<KeyT, NullType>(d_temp_storage, temp_storage_bytes, d_keys.Current(), d_keys.Alternate(), nullptr, nullptr, &sel,   \
+                                        num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit, end_bit, sizeof(#DESC) > 1, true, \
+                                        stream, debug_synchronous);                                                                         \
+    if (d_temp_storage && e == cudaSuccess) d_keys.selector ^= sel;                                                                         \
+    return e;                                                                                                                               \
+  }                                                                                                                                         \
+  template <typename KeyT>                                                                                                                  \
+  static cudaError_t SortKeys##DESC(void* d_temp_storage, size_t& temp_storage_bytes, const KeyT* d_keys_in, KeyT* d_keys_out,              \
+                                    int num_items, int num_segments, const int* d_begin_offsets, const int* d_end_offsets,                  \
+                                    int begin_bit = 0, int end_bit = sizeof(KeyT) * 8, cudaStream_t stream = 0,                             \
+                                    bool debug_synchronous = false) {                                                                       \
+    return run<KeyT, NullType>(d_temp_storage, temp_storage_bytes, const_cast<KeyT*>(d_keys_in), d_keys_out, nullptr, nullptr, nullptr,     \
+                               num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit, end_bit, sizeof(#DESC) > 1, false,       \
+                               stream, debug_synchronous);                                                                                  \
+  }
+  B200_CUB_SEG_ENTRY()
+  B200_CUB_SEG_ENTRY(Descending)
+#undef B200_CUB_SEG_ENTRY
+};
 }  // namespace cub

@@ -137,6 +137,30 @@ int oracle_lsb_sort(const void* keys_in, const void* vals_in, uint64_t n, int ke
   return 0;
 }
 
+/*
+ * Segmented stable sort: every segment [begin[i], end[i]) sorted on its own, the rest of the array copied through.
+ * Follows the reference's own CPU solution for cub::DeviceSegmentedRadixSort, lsb/cub/test/test_device_radix_sort.cu:669-676
+ * (per segment: std::stable_sort, descending = reverse + stable_sort + reverse, which keeps equal keys in input order), i.e.
+ * oracle_lsb_sort applied to each slice.  offsets are int64 here.
+ */
+int oracle_segmented_sort(const void* keys_in, const void* vals_in, uint64_t n, int key_type, int value_bytes,
+                          uint64_t num_segments, const int64_t* begin, const int64_t* end,
+                          int begin_bit, int end_bit, int descending, void* keys_out, void* vals_out) {
+  const int kbytes = key_bits_of(key_type) / 8;
+  memcpy(keys_out, keys_in, n * (uint64_t)kbytes);
+  if (value_bytes) memcpy(vals_out, vals_in, n * (uint64_t)value_bytes);
+  for (uint64_t i = 0; i < num_segments; ++i) {
+    if (end[i] <= begin[i]) continue;                       /* empty segment (device_segmented_radix_sort.cuh:150) */
+    if (begin[i] < 0 || (uint64_t)end[i] > n) return -3;
+    const uint64_t b = (uint64_t)begin[i], c = (uint64_t)(end[i] - begin[i]);
+    const int rc = oracle_lsb_sort((const char*)keys_in + b * kbytes, value_bytes ? (const char*)vals_in + b * value_bytes : NULL, c, key_type,
+                                   value_bytes, begin_bit, end_bit, descending, (char*)keys_out + b * kbytes,
+                                   value_bytes ? (char*)vals_out + b * value_bytes : NULL, 1);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------------------
  * Unstable MSB "hybrid radix sort" = rdxsrt_unstable_sort (msb/src/sort/gpu_radix_sort.h:187-507).
  *   pass loop, 8-bit digits from the most significant byte down      gpu_radix_sort.h:205,279-351,366-486

@@ -22,6 +22,8 @@ class Oracle:
         lib.oracle_lsb_sort.argtypes = [vp, vp, u64, i32, i32, i32, i32, i32, vp, vp, i32]
         lib.oracle_msb_sort.restype = i32
         lib.oracle_msb_sort.argtypes = [vp, vp, u64, i32, i32, vp, vp, i32, i32]
+        lib.oracle_segmented_sort.restype = i32
+        lib.oracle_segmented_sort.argtypes = [vp, vp, u64, i32, i32, u64, vp, vp, i32, i32, i32, vp, vp]
         lib.oracle_gen_keys.restype = None
         lib.oracle_gen_keys.argtypes = [vp, u64, u64, u64, i32, u64, i32, u64]
         lib.oracle_digest.restype = None
@@ -49,6 +51,19 @@ class Oracle:
         vo = np.empty_like(vals) if vals is not None else None
         rc = self.lib.oracle_lsb_sort(self._p(keys), self._p(vals), keys.size, KT[key_type], 0 if vals is None else vals.dtype.itemsize,
                                       begin_bit, kb if end_bit is None else end_bit, int(descending), self._p(ko), self._p(vo), threads)
+        assert rc == 0
+        return ko, vo
+
+    def segmented_sort(self, keys, vals, begin, end, key_type="u32", begin_bit=0, end_bit=None, descending=False):
+        """Every [begin[i], end[i]) sorted stably on its own; elements outside all segments copied through."""
+        keys = np.ascontiguousarray(keys)
+        begin = np.ascontiguousarray(begin, dtype=np.int64); end = np.ascontiguousarray(end, dtype=np.int64)
+        kb = keys.dtype.itemsize * 8
+        ko = np.empty_like(keys)
+        vo = np.empty_like(vals) if vals is not None else None
+        rc = self.lib.oracle_segmented_sort(self._p(keys), self._p(vals), keys.size, KT[key_type], 0 if vals is None else vals.dtype.itemsize,
+                                            begin.size, self._p(begin), self._p(end), begin_bit, kb if end_bit is None else end_bit,
+                                            int(descending), self._p(ko), self._p(vo))
         assert rc == 0
         return ko, vo
 

@@ -19,7 +19,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    for s in ("b200_lsb_sort", "b200_msb_sort", "b200_msb_sort_host", "b200_lsb_sort_host", "b200_msd_histogram",
+    for s in ("b200_lsb_sort", "b200_segmented_sort", "b200_msb_sort", "b200_msb_sort_host", "b200_lsb_sort_host", "b200_msd_histogram",
               "b200_range_partition", "b200_util_generate_keys", "b200_util_iota", "b200_util_check", "b200_version"):
         assert s in syms
 
@@ -64,6 +64,20 @@ def test_size_queries_and_argument_errors_need_no_gpu():
             assert lib.b200_msb_sort(None, None, n, None, None, kt, vb, None, ctypes.byref(w), None, None, None) == 0
             assert w.value >= 256
         prev = n
+    # segmented sort: the same two-phase protocol, plus two on-chip work lists sized by the segment count
+    lib.b200_segmented_sort.restype = i32
+    lib.b200_segmented_sort.argtypes = [vp, ctypes.POINTER(sz), vp, vp, vp, vp, ctypes.POINTER(i32), u64, ctypes.c_uint32, vp, vp, i32,
+                                        i32, i32, i32, i32, i32, i32, vp]
+    for n, ns in ((0, 0), (1000, 1), (1 << 20, 5000), (1 << 28, 1 << 20)):
+        b = sz(0); b1 = sz(0); b0 = sz(0)
+        assert lib.b200_segmented_sort(None, ctypes.byref(b), None, None, None, None, None, n, ns, None, None, 4, 0, 4, 0, 32, 0, 1, None) == 0
+        assert lib.b200_lsb_sort(None, ctypes.byref(b1), None, None, None, None, None, n, 0, 4, 0, 32, 0, 1, None) == 0
+        assert b.value >= b1.value + 2 * 16 * ns
+        assert lib.b200_segmented_sort(None, ctypes.byref(b0), None, None, None, None, None, n, ns, None, None, 4, 0, 4, 0, 32, 0, 0, None) == 0
+        assert b0.value >= b.value
+    b = sz(0)
+    assert lib.b200_segmented_sort(None, ctypes.byref(b), None, None, None, None, None, 10, 1, None, None, 2, 0, 0, 0, 32, 0, 1, None) != 0   # bad offset width
+    assert lib.b200_segmented_sort(None, ctypes.byref(b), None, None, None, None, None, 1 << 32, 1, None, None, 8, 0, 0, 0, 32, 0, 1, None) != 0   # n >= 2^32
     b = sz(0)
     assert lib.b200_lsb_sort(None, ctypes.byref(b), None, None, None, None, None, 10, 99, 0, 0, 32, 0, 1, None) != 0   # bad key type
     assert lib.b200_lsb_sort(None, ctypes.byref(b), None, None, None, None, None, 10, 0, 3, 0, 32, 0, 1, None) != 0    # bad value width

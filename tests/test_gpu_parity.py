@@ -457,3 +457,114 @@ def test_key_range_probe_paths(gs, oracle, kt, vb):
         if vb:
             rv = host(r.sorted_values, v.dtype)
             assert same_bits(k[rv.astype(np.int64)], ek), name
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# segmented sort (cub::DeviceSegmentedRadixSort call shape) vs the oracle: bit-exact keys and values inside every segment.
+# Families of lsb/cub/test/test_device_radix_sort.cu:1003-1026 (segment counts n_seg -> ceil(n_seg/32) ... with random
+# lengths, single segment), plus segments larger than the on-chip capacity, gaps, empty segments and 64-bit offsets.
+# ------------------------------------------------------------------------------------------------------------------
+def run_segmented(gs, k, v, kt, begin, end, descending=False, begin_bit=0, end_bit=None, overwrite=True, offset_dtype=np.int32):
+    n = k.size
+    k0, k1 = dev(k), torch.empty_like(dev(k))
+    v0 = dev(v); v1 = torch.empty_like(v0) if v is not None else None
+    k1.zero_()
+    db = torch.from_numpy(np.ascontiguousarray(begin, dtype=offset_dtype)).cuda()
+    de = torch.from_numpy(np.ascontiguousarray(end, dtype=offset_dtype)).cuda()
+    S = gs.DeviceSegmentedRadixSort
+    fn = {(False, False): S.SortKeys, (False, True): S.SortKeysDescending, (True, False): S.SortPairs, (True, True): S.SortPairsDescending}[(v is not None, descending)]
+    ns = len(begin)
+    if overwrite:
+        dk = gs.DoubleBuffer(k0, k1); dv = gs.DoubleBuffer(v0, v1) if v is not None else None
+        args = (dk, dv, n, ns, db, de) if v is not None else (dk, n, ns, db, de)
+        kw = dict(begin_bit=begin_bit, end_bit=end_bit, key_type=KT_ID[kt])
+    else:
+        args = (k0, v0, n, ns, db, de) if v is not None else (k0, n, ns, db, de)
+        kw = dict(begin_bit=begin_bit, end_bit=end_bit, key_type=KT_ID[kt], d_keys_out=k1)
+        if v is not None:
+            kw["d_values_out"] = v1
+    tb = fn(None, *args, **kw)
+    temp = torch.empty(tb, dtype=torch.uint8, device="cuda")
+    fn(temp, *args, **kw)
+    torch.cuda.synchronize()
+    if overwrite:
+        return host(dk.Current(), k.dtype), host(dv.Current(), v.dtype) if v is not None else None
+    assert np.array_equal(host(k0, k.dtype).view(np.uint8), k.view(np.uint8)), "pointer overload must not touch the input"
+    return host(k1, k.dtype), host(v1, v.dtype) if v is not None else None
+
+
+def assert_segments_equal(rk, rv, ek, ev, begin, end):
+    """Only elements inside a segment are specified (as in CUB)."""
+    covered = np.zeros(rk.size, dtype=bool)
+    for b, e in zip(begin, end):
+        if e > b:
+            covered[b:e] = True
+    assert same_bits(rk[covered], ek[covered])
+    if rv is not None:
+        assert np.array_equal(rv[covered], ev[covered])
+
+
+def cub_segments(n, num_segments, seed):
+    rng = np.random.default_rng(seed)
+    expected = (n + num_segments - 1) // max(num_segments, 1)
+    off = np.zeros(num_segments + 1, dtype=np.int64)
+    cur = 0
+    for i in range(num_segments):
+        off[i] = cur
+        cur = min(cur + int(rng.integers(0, 2 * expected + 1)), n)
+    off[num_segments] = n
+    return off
+
+
+@pytest.mark.parametrize("kt,vb", [("u32", 0), ("u32", 4), ("u64", 8), ("f32", 4), ("i64", 0), ("f64", 4)])
+@pytest.mark.parametrize("descending", [False, True])
+def test_segmented_cub_families(gs, oracle, kt, vb, descending):
+    n = 300000
+    k = raw_keys(oracle, n, kt, seed=4, dist="entropy", param=2)
+    v = iota(n, vb)
+    num_segments = 5000
+    while True:
+        off = cub_segments(n, num_segments, seed=num_segments)
+        ek, ev = oracle.segmented_sort(k, v, off[:-1], off[1:], key_type=kt, descending=descending)
+        rk, rv = run_segmented(gs, k, v, kt, off[:-1], off[1:], descending=descending)
+        assert_segments_equal(rk, rv, ek, ev, off[:-1], off[1:])
+        if num_segments == 1:
+            break
+        num_segments = (num_segments + 31) // 32 if num_segments > 32 else 1
+
+
+@pytest.mark.parametrize("kt,vb", [("u32", 4), ("u64", 0), ("u64", 4)])
+@pytest.mark.parametrize("overwrite", [True, False])
+def test_segmented_mixed_sizes_gaps_and_empty(gs, oracle, kt, vb, overwrite):
+    """Segments from 1 key to far beyond the on-chip capacity in one call, with gaps, empty segments and int64 offsets."""
+    n = 1 << 21
+    k = raw_keys(oracle, n, kt, seed=9)
+    v = iota(n, vb)
+    begin = np.array([0, 5, 700, 700, 10000, 50000, 60000, 400000, 1500000, 2000000, 2097151], dtype=np.int64)
+    end = np.array([1, 600, 700, 650, 14000, 59000, 390000, 1400000, 1500007, 2097100, 2097152], dtype=np.int64)
+    ek, ev = oracle.segmented_sort(k, v, begin, end, key_type=kt)
+    rk, rv = run_segmented(gs, k, v, kt, begin, end, overwrite=overwrite, offset_dtype=np.int64)
+    assert_segments_equal(rk, rv, ek, ev, begin, end)
+
+
+def test_segmented_bit_subrange_and_duplicates(gs, oracle):
+    n = 200000
+    k = raw_keys(oracle, n, "u32", seed=3, dist="entropy", param=4)     # heavy duplicates
+    v = iota(n, 4)
+    off = cub_segments(n, 40, seed=7)
+    for bb, eb in ((0, 32), (8, 24), (15, 17), (5, 5)):
+        ek, ev = oracle.segmented_sort(k, v, off[:-1], off[1:], key_type="u32", begin_bit=bb, end_bit=eb)
+        rk, rv = run_segmented(gs, k, v, "u32", off[:-1], off[1:], begin_bit=bb, end_bit=eb, overwrite=False)
+        assert_segments_equal(rk, rv, ek, ev, off[:-1], off[1:])
+
+
+def test_segmented_many_tiny_segments(gs, oracle):
+    """2^17 segments of 0..16 keys: one launch, no per-segment host work."""
+    n = 1 << 20
+    k = raw_keys(oracle, n, "u32", seed=11)
+    v = iota(n, 4)
+    off = cub_segments(n, 1 << 17, seed=5)
+    ek, ev = oracle.segmented_sort(k, v, off[:-1], off[1:], key_type="u32")
+    rk, rv = run_segmented(gs, k, v, "u32", off[:-1], off[1:])
+    assert_segments_equal(rk, rv, ek, ev, off[:-1], off[1:])
+    rk, rv = run_segmented(gs, k, None, "u32", np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64))      # no segments: a no-op

@@ -133,3 +133,50 @@ def test_oracle_matches_reference_golden(oracle):
             assert _sha(ko) == c["keys_sha256"], c
             if v is not None:
                 assert _sha(vo) == c["values_sha256"], c
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# segmented sort oracle (cub::DeviceSegmentedRadixSort; CPU solution of lsb/cub/test/test_device_radix_sort.cu:669-676)
+# ------------------------------------------------------------------------------------------------------------------
+def cub_segments(n, num_segments, seed):
+    """Segment offsets the way the reference test draws them (InitializeSegments, lsb/cub/test/test_util.h:1475-1494):
+    lengths uniform in [0, 2 * expected], clipped at n; the last segment takes the remainder."""
+    rng = np.random.default_rng(seed)
+    expected = (n + num_segments - 1) // max(num_segments, 1)
+    off = np.zeros(num_segments + 1, dtype=np.int64)
+    cur = 0
+    for i in range(num_segments):
+        off[i] = cur
+        cur = min(cur + int(rng.integers(0, 2 * expected + 1)), n)
+    off[num_segments] = n
+    return off
+
+
+@pytest.mark.parametrize("key_type", ["u32", "i64", "f32"])
+@pytest.mark.parametrize("descending", [False, True])
+def test_segmented_oracle_matches_per_segment_stable_sort(oracle, key_type, descending):
+    n, ns = 20000, 37
+    k = raw_keys(oracle, n, key_type, seed=5, dist="entropy", param=3)
+    v = np.arange(n, dtype=np.uint32)
+    off = cub_segments(n, ns, seed=1)
+    ko, vo = oracle.segmented_sort(k, v, off[:-1], off[1:], key_type=key_type, descending=descending)
+    tw = twiddle_np(k, key_type)
+    for i in range(ns):
+        b, e = int(off[i]), int(off[i + 1])
+        t = tw[b:e]
+        order = np.argsort(~t if descending else t, kind="stable")
+        assert np.array_equal(ko[b:e].view(np.uint8), k[b:e][order].view(np.uint8))
+        assert np.array_equal(vo[b:e], v[b:e][order])
+
+
+def test_segmented_oracle_gaps_and_empty_segments(oracle):
+    n = 5000
+    k = raw_keys(oracle, n, "u32", seed=2)
+    begin = np.array([10, 100, 100, 4000, 300], dtype=np.int64)
+    end = np.array([60, 100, 90, 5000, 1000], dtype=np.int64)        # second and third are empty (end <= begin)
+    ko, _ = oracle.segmented_sort(k, None, begin, end, key_type="u32")
+    exp = k.copy()
+    for b, e in zip(begin, end):
+        if e > b:
+            exp[b:e] = np.sort(k[b:e])
+    assert np.array_equal(ko, exp)
