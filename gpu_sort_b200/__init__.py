@@ -54,8 +54,9 @@ def _load():
     lib.b200_error_string.argtypes = [i32]
     lib.b200_lsb_sort.restype = i32
     lib.b200_lsb_sort.argtypes = [vp, P(sz), vp, vp, vp, vp, P(i32), u64, i32, i32, i32, i32, i32, i32, vp]
-    lib.b200_segmented_sort.restype = i32
-    lib.b200_segmented_sort.argtypes = [vp, P(sz), vp, vp, vp, vp, P(i32), u64, ctypes.c_uint32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    if hasattr(lib, "b200_segmented_sort") or not os.environ.get("B200SORT_LIB"):     # (older A/B variant builds lack it)
+        lib.b200_segmented_sort.restype = i32
+        lib.b200_segmented_sort.argtypes = [vp, P(sz), vp, vp, vp, vp, P(i32), u64, ctypes.c_uint32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.b200_msb_sort.restype = i32
     lib.b200_msb_sort.argtypes = [vp, vp, u64, vp, vp, i32, i32, vp, P(sz), vp, P(vp), P(vp)]
     lib.b200_msb_sort_bits.restype = i32

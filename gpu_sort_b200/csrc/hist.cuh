@@ -87,7 +87,10 @@ static __global__ void __launch_bounds__(RADIX) scan_bins_kernel(unsigned long l
 // A group = HIST_GROUP consecutive entries of the tile list (segments are contiguous in the list); one CTA handles a
 // whole group, so the running counts live in registers.  group_carry_kernel then chains the groups.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int HIST_GROUP = 16;
+#ifndef B200_HIST_GROUP
+#define B200_HIST_GROUP 16
+#endif
+constexpr int HIST_GROUP = B200_HIST_GROUP;
 
 struct TileHistArgs {
   const void* keys;
@@ -98,6 +101,7 @@ struct TileHistArgs {
   int shift; uint32_t mask; int tw_in; Twiddle tw;
   const uint32_t* splitters; int num_parts;     // range mode: digit = #{ j < num_parts-1 : splitters[j] <= (key >> shift) }
   unsigned long long* key_or; unsigned long long* key_and;   // PROBE: OR / AND of all transformed keys are accumulated here
+  uint32_t* ticket;                            // zeroed counter: groups are handed out dynamically (nullptr: round-robin)
 };
 
 template <typename K, bool RANGE, bool PROBE>
@@ -122,7 +126,14 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
     else d = range_part(rl, (uint32_t)(k >> shift), cshift);
     atomicAdd(&sh[d], 1u);
   };
-  for (uint32_t g = blockIdx.x; g < num_groups; g += gridDim.x) {
+  __shared__ uint32_t s_next;
+  for (uint32_t g = blockIdx.x;; g += gridDim.x) {
+    if (a.ticket != nullptr) {       // dynamic hand-out: with ~3.5 groups per CTA a static deal leaves 13 % of the CTAs idle in the last round
+      if (tid == 0) s_next = atomicAdd(a.ticket, 1u);
+      __syncthreads();
+      g = s_next;                    // (the barriers of the tile loop order this read before the next hand-out)
+    }
+    if (g >= num_groups) break;
     const uint32_t t0 = g * HIST_GROUP, t1 = min(t0 + HIST_GROUP, num_tiles);
     uint32_t run = 0, acc = 0, flag = 0, cur_seg = a.descs[t0].seg;      // digit owners (tid < 256)
     for (uint32_t t = t0; t < t1; ++t) {

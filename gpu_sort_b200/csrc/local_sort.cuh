@@ -89,7 +89,7 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
   using V = typename ValType<VB>::type;
   constexpr int NWARPS = THREADS / 32;
   const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-  const int rows = (int)((cnt + THREADS - 1) / THREADS);
+  const int rows = (int)((cnt + THREADS - 1) / THREADS);      // block-uniform: rows past the bucket are skipped without per-thread tests
   constexpr int MAXBITS = CountBits<K, VB>::value;
   constexpr int NSEG = CountSmem<THREADS, MAXBITS>::NSEG;
   int cbits = 32 - __clz(cnt);
@@ -129,14 +129,16 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
   // ---- exclusive prefix over the counter words; thread t owns the NSEG consecutive 4-word groups t*NSEG ..
   {
     // per-word nibble sums (a word holds <= 8 * 15 keys; a 4-word group can exceed 255, so the words are summed separately)
-    auto wsum = [](uint32_t x) { const uint32_t t = (x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu); return (t * 0x01010101u) >> 24; };
+    // acc + the eight nibbles of x: two byte-wise dot products with ones (IDP.4A accumulates for free; measured 2.4 % of a
+    // 2^28-key sort against the and/shift/multiply form)
+    auto nadd = [](uint32_t x, uint32_t acc) { return __dp4a(x & 0x0F0F0F0Fu, 0x01010101u, __dp4a((x >> 4) & 0x0F0F0F0Fu, 0x01010101u, acc)); };
     uint32_t tsum = 0;
 #pragma unroll
     for (int g = 0; g < NSEG; ++g) {
       const uint32_t gi = tid * NSEG + g;
       if (gi < groups) {
         const uint4 q = reinterpret_cast<const uint4*>(cs.nib)[gi];
-        tsum += wsum(q.x) + wsum(q.y) + wsum(q.z) + wsum(q.w);
+        tsum = nadd(q.w, nadd(q.z, nadd(q.y, nadd(q.x, tsum))));
       }
     }
     uint32_t inc = tsum;
@@ -160,10 +162,10 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
       const uint32_t gi = tid * NSEG + g;
       if (gi < groups) {
         const uint4 q = reinterpret_cast<const uint4*>(cs.nib)[gi];
-        const uint32_t p0 = run; run += wsum(q.x);
-        const uint32_t p1 = run; run += wsum(q.y);
-        const uint32_t p2 = run; run += wsum(q.z);
-        const uint32_t p3 = run; run += wsum(q.w);
+        const uint32_t p0 = run; run = nadd(q.x, run);
+        const uint32_t p1 = run; run = nadd(q.y, run);
+        const uint32_t p2 = run; run = nadd(q.z, run);
+        const uint32_t p3 = run; run = nadd(q.w, run);
         reinterpret_cast<uint2*>(cs.wpre)[gi] = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
       }
     }
@@ -171,7 +173,26 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
   __syncthreads();
 
   // ---- scatter to cell start + rank in cell
-  uint32_t cell0[ROWS];          // packed: start of the key's cell | keys in the cell << 16
+  uint32_t cell0[ROWS];          // packed: start of the key's cell | keys in the cell << 16 (only where cells hold distinct keys)
+  const bool order_cells = STABLE || hi - lo > cbits;
+#if B200_LOCAL_LEAN_EXACT
+  if (!order_cells) {            // exact cells: nothing else to record
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const uint32_t idx = j * THREADS + tid;
+      if (j < rows && idx < cnt) {
+        const uint32_t v = (uint32_t)(key[j] >> vshift) & vmask;
+        const uint32_t lowc = cs.nib[v >> 3] & ((1u << ((v & 7u) * 4u)) - 1u);
+        const uint32_t c0 = __dp4a(lowc & 0x0F0F0F0Fu, 0x01010101u, __dp4a((lowc >> 4) & 0x0F0F0F0Fu, 0x01010101u, (uint32_t)cs.wpre[v >> 3]));
+        const uint32_t q = pos[j] + c0;
+        sk[aoff + q] = key[j];
+        if (VB) sv[q] = val[j];      // every thread read its values at the top (a barrier ago): the slot is free
+      }
+    }
+    __syncthreads();
+    return true;
+  }
+#endif
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) {
     const uint32_t idx = j * THREADS + tid;
@@ -179,10 +200,8 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
       const uint32_t v = (uint32_t)(key[j] >> vshift) & vmask;
       const uint32_t sh = (v & 7u) * 4u;
       const uint32_t wd = cs.nib[v >> 3];
-      uint32_t below = wd & ((1u << sh) - 1u);
-      below = (below & 0x0F0F0F0Fu) + ((below >> 4) & 0x0F0F0F0Fu);
-      below = (below * 0x01010101u) >> 24;
-      const uint32_t c0 = (uint32_t)cs.wpre[v >> 3] + below;
+      const uint32_t lowc = wd & ((1u << sh) - 1u);
+      const uint32_t c0 = __dp4a(lowc & 0x0F0F0F0Fu, 0x01010101u, __dp4a((lowc >> 4) & 0x0F0F0F0Fu, 0x01010101u, (uint32_t)cs.wpre[v >> 3]));
       cell0[j] = c0 | (((wd >> sh) & 15u) << 16);
       pos[j] += c0;
       sk[aoff + pos[j]] = key[j];
@@ -191,7 +210,7 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
   }
 
   // ---- keys that share a cell: order them by direct comparison on bits [lo, hi) (and the input index when stable)
-  if (STABLE || hi - lo > cbits) {
+  if (order_cells) {
     __syncthreads();
     uint32_t npos[ROWS];
     const int up = (int)sizeof(K) * 8 - hi, dn = up + lo;
@@ -375,6 +394,9 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
 
 #ifndef B200_LOCAL_OCC384
 #define B200_LOCAL_OCC384 2
+#endif
+#ifndef B200_LOCAL_LEAN_EXACT
+#define B200_LOCAL_LEAN_EXACT 1
 #endif
 #ifndef B200_LOCAL_VEC_OUT
 #define B200_LOCAL_VEC_OUT 1

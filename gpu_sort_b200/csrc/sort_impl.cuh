@@ -36,6 +36,9 @@ struct Cfg {
 #define B200_IPT_NUM 1
 #define B200_IPT_DEN 1
 #endif
+#ifndef B200_HIST_TICKET
+#define B200_HIST_TICKET 1
+#endif
 #ifndef B200_LOCAL_IPT32
 #define B200_LOCAL_IPT32 12
 #endif
@@ -199,11 +202,43 @@ inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
   for (int i = 0; i < 4; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
 }
 
-// Pinned 16-byte landing zone for the key-range probe (one per host thread).
+// Pinned landing zone for the key-range probe: key_or, key_and, {probe_single, -} (one per host thread).
 inline unsigned long long* probe_buffer() {
   static thread_local unsigned long long* p = nullptr;
-  if (!p && cudaHostAlloc(reinterpret_cast<void**>(&p), 2 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+  if (!p && cudaHostAlloc(reinterpret_cast<void**>(&p), 4 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) p = nullptr;
   return p;
+}
+inline cudaEvent_t probe_event() {
+  static thread_local cudaEvent_t ev = nullptr;
+  if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+  return ev;
+}
+// Runs right after the level-0 histogram of a probing sort.  If the keys agree on leading bits of the sorted window, the sort
+// that is already enqueued behind this kernel would waste whole levels on single-bucket digits: empty its work lists so that
+// every kernel behind finds nothing to do (they all read their counts from device memory); the host, which learns the same
+// from the read-back, then enqueues the sort again on the narrower window.
+//   FROM_HIST: the OR / AND of the leading digit follow from WHICH level-0 buckets are non-empty (no per-key work in the
+//   histogram kernel); the bits below the digit count as differing.  A single non-empty bucket says nothing about the lower
+//   bits: key_or = key_and = 0 and probe_single = 1 ask the host for a round with the exact per-key OR / AND.
+template <bool FROM_HIST>
+static __global__ void __launch_bounds__(RADIX) probe_eval_kernel(MsbCounters* c, const uint32_t* seg_hist, int shift0, int begin_bit, int end_bit) {
+  __shared__ uint32_t s_or, s_and, s_cnt;
+  if (FROM_HIST) {
+    if (threadIdx.x == 0) { s_or = 0; s_and = 0xFFFFFFFFu; s_cnt = 0; }
+    __syncthreads();
+    if (seg_hist[threadIdx.x] != 0) { atomicOr(&s_or, threadIdx.x); atomicAnd(&s_and, threadIdx.x); atomicAdd(&s_cnt, 1u); }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  if (FROM_HIST) {
+    const unsigned long long low = (1ull << shift0) - 1ull;
+    c->probe_single = s_cnt <= 1 ? 1u : 0u;
+    c->key_or = s_cnt <= 1 ? 0ull : (((unsigned long long)s_or << shift0) | low);
+    c->key_and = s_cnt <= 1 ? 0ull : ((unsigned long long)s_and << shift0);
+  }
+  unsigned long long diff = c->key_or ^ c->key_and;
+  diff &= (end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1ull)) & ~((1ull << begin_bit) - 1ull);
+  if (end_bit > begin_bit && ((diff >> (end_bit - 1)) & 1ull) == 0ull) { c->num_tiles[0] = 0; c->num_segs[0] = 0; }
 }
 constexpr uint64_t PROBE_MIN_ITEMS = 1ull << 22;     // below this the extra stream synchronisation costs more than it can save
 
@@ -247,130 +282,143 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     return launch_local<K, VB, ALGO_LSD, ORDERED>(la, 1, s);
   }
 
-  B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
-  {
-    ProfScope prof("msb_sched", s);
-    if (segin != nullptr) {
-      SegInitArgs sa{};
-      sa.begin = segin->begin; sa.end = segin->end; sa.num_segments = segin->num_segments; sa.offset_bytes = segin->offset_bytes;
-      sa.n = n; sa.segs = w.segs0; sa.max_segs = w.max_segs; sa.direct = segin->direct; sa.direct_small = segin->direct_small;
-      sa.ctr = ctr; sa.local_cap = C::LOCAL_CAP; sa.small_cap = C::SMALL_CAP; sa.end_bit = end_bit;
-      const int sgrid = (int)std::min<uint32_t>((segin->num_segments + 255) / 256, (uint32_t)sms * 8);
-      seg_init_kernel<<<std::max(sgrid, 1), 256, 0, s>>>(sa);
-      seg_clamp_kernel<<<1, 1, 0, s>>>(ctr, w.max_segs);
-    } else {
-      msb_init_kernel<<<1, 32, 0, s>>>(w.segs0, ctr, n);
-    }
-    scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(w.segs0, &ctr->num_segs[0], w.tile_base, &ctr->num_tiles[0], w.max_tiles, &ctr->error, C::TILE);
-    fill_descs_kernel<<<sms * 2, 256, 0, s>>>(w.segs0, w.tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], w.descs, C::TILE);
-  }
   // Key-range probe: the level-0 histogram also ORs / ANDs every key.  Leading bits on which all keys agree cannot influence
   // the order, so the digit windows start below them (small-range keys, e.g. indices below 2^20 in 64-bit keys, would
-  // otherwise spend whole sweeps on single-bucket levels).  Costs one 16-byte read-back + stream synchronisation; skipped for
-  // small inputs and while the stream is being captured into a CUDA graph.
-  bool probe = n >= PROBE_MIN_ITEMS && levels > 1 && segin == nullptr;
+  // otherwise spend whole sweeps on single-bucket levels).  The sort is enqueued optimistically on the full window; a one-thread
+  // kernel behind the level-0 histogram empties the work lists if the window turns out too wide, and the host -- after one
+  // event wait at the END of the enqueue, when the device is busy -- enqueues the narrower sort.  Skipped for small inputs and
+  // while the stream is being captured into a CUDA graph.
+  // probe = 1: OR / AND of the leading digit from the level-0 histogram (free); 2: exact per-key OR / AND; 0: none
+  int probe = (n >= PROBE_MIN_ITEMS && levels > 1 && segin == nullptr) ? 1 : 0;
+  { static const char* e = getenv("B200SORT_PROBE"); if (e && e[0] == '0') probe = 0; }      // measurement switch
   if (probe) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone || probe_buffer() == nullptr) probe = false;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone || probe_buffer() == nullptr || probe_event() == nullptr) probe = 0;
   }
-  for (int L = 0; L < levels; ++L) {
-    const int shift = std::max(begin_bit, end_bit - 8 * (L + 1));
-    const int nb = (end_bit - 8 * L) - shift;
-    const uint32_t mask = (1u << nb) - 1u;
-    Seg* cur = (L & 1) ? w.segs1 : w.segs0;
-    Seg* nxt = (L & 1) ? w.segs0 : w.segs1;
-    const int ib = in_buf(L), ob = out_buf(L);
-
-    { ProfScope prof("msb_sched", s); level_prep_kernel<<<sms * 2, 512, 0, s>>>(w.seg_hist, &ctr->num_segs[L]); }
-    TileHistArgs ha{};
-    ha.keys = bufk[ib]; ha.descs = w.descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
-    ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist;
-    ha.tile_cnt = w.tile_cnt;
-    ha.shift = shift; ha.mask = mask; ha.tw_in = (L == 0) ? twid : 0; ha.tw = tw;
-    ha.key_or = &ctr->key_or; ha.key_and = &ctr->key_and;
-    const int hgrid = (int)std::min<uint32_t>(w.max_groups, (uint32_t)sms * 4);
-    if (L == 0 && probe) {
-      { ProfScope prof("tile_hist", s); tile_hist_kernel<K, false, true><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
-      unsigned long long* hp = probe_buffer();
-      B200_CHECK(cudaMemcpyAsync(hp, &ctr->key_or, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-      B200_CHECK(cudaStreamSynchronize(s));
-      probe = false;
-      unsigned long long diff = hp[0] ^ hp[1];                                  // bits on which the keys differ
-      diff &= (end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1ull)) & ~((1ull << begin_bit) - 1ull);
-      int new_end = begin_bit;
-      while (new_end < end_bit && (diff >> new_end) != 0) ++new_end;           // highest differing bit + 1
-      if (new_end < end_bit) {
-        // restart with the narrower window (the level-0 histogram just taken used the wrong digit)
-        end_bit = new_end;
-        levels = (end_bit - begin_bit + 7) / 8;
-        if (fin_in < 0) fin = levels & 1;
-        if (levels == 0) {                // all keys equal on the sorted bits: the input order is the (stable) answer
-          if (fin_out) *fin_out = fin;
-          if (fin != 0) {
-            B200_CHECK(cudaMemcpyAsync(bufk[fin], bufk[0], n * sizeof(K), cudaMemcpyDeviceToDevice, s));
-            if (VB) B200_CHECK(cudaMemcpyAsync(bufv[fin], bufv[0], n * sizeof(V), cudaMemcpyDeviceToDevice, s));
-          }
-          return cudaSuccess;
-        }
-        L = -1;
-        continue;
-      }
-    } else {
-      ProfScope prof("tile_hist", s); tile_hist_kernel<K, false, false><<<hgrid, HIST_THREADS, 0, s>>>(ha);
-    }
-    { ProfScope prof("msb_sched", s); group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(w.group_tail, w.group_flag, w.carry, &ctr->num_tiles[L]); }
-
-    ClassifyArgs ca{};
-    ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = w.seg_hist; ca.bins = w.bins;
-    ca.next_segs = nxt; ca.num_next_ptr = &ctr->num_segs[L + 1]; ca.max_segs = w.max_segs;
-    // buckets of this level: which on-chip algorithm.  More than 16 bits left -> one-shot counting sort; otherwise the unstable
-    // keys-only engine still prefers it for its large unmerged buckets (one cell per key value: half the shared-memory traffic of
-    // two LSD passes); merged runs, small buckets and the stable engine take the LSD kernels
-    int list = (shift - begin_bit > 16) ? ALGO_COUNT : ALGO_LSD;
-    const bool count_big = !ORDERED && VB == 0 && sizeof(K) == 4 && list == ALGO_LSD;
-    { static const char* e = getenv("B200SORT_LOCAL"); if (e) list = (e[0] == 'c') ? ALGO_COUNT : ALGO_LSD; }
-    const int big_list = count_big ? ALGO_COUNT : list;
-    ca.locals = w.locals[big_list]; ca.num_locals_ptr = &ctr->num_locals[big_list]; ca.max_locals = w.max_locals;
-    if (list == ALGO_LSD) { ca.locals_small = w.locals[3]; ca.num_small_ptr = &ctr->num_locals[2]; ca.small_cap = C::SMALL_CAP; }
-    if (count_big) { ca.locals_merged = w.locals[ALGO_LSD]; ca.num_merged_ptr = &ctr->num_locals[ALGO_LSD]; }   // merged runs need LSD passes
-    ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
-    ca.local_cap = C::LOCAL_CAP; ca.merge_cap = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP : C::MERGE_CAP;
-    ca.out_buf = (uint32_t)ob;
-    const int cgrid = (int)std::min<uint32_t>((w.max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
-    { ProfScope prof("msb_sched", s); classify_kernel<<<(L == 0 && segin == nullptr) ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca); }
-
-    ScatterArgs pa{};
-    pa.keys_in = bufk[ib]; pa.keys_out = bufk[ob]; pa.vals_in = bufv[ib]; pa.vals_out = bufv[ob];
-    pa.descs = w.descs; pa.num_tiles_ptr = &ctr->num_tiles[L];
-    pa.bins = w.bins; pa.tile_off = w.tile_off; pa.carry = w.carry; pa.tile_cnt = w.tile_cnt;
-    pa.shift = shift; pa.mask = mask; pa.tw_in = (L == 0) ? twid : 0; pa.tw_out = (shift == begin_bit) ? twid : 0; pa.tw = tw;
-    B200_CHECK((launch_scatter<K, VB, MODE_SEG, ORDERED>(pa, w.max_tiles, s)));
-
-    if (L + 1 < levels) {
+  for (;;) {      // the optimistic enqueue; then, only if the probe asks: (an exact-probe round and) the narrowed sort
+    B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
+    {
       ProfScope prof("msb_sched", s);
-      scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(nxt, &ctr->num_segs[L + 1], w.tile_base, &ctr->num_tiles[L + 1], w.max_tiles, &ctr->error, C::TILE);
-      fill_descs_kernel<<<sms * 2, 256, 0, s>>>(nxt, w.tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], w.descs, C::TILE);
+      if (segin != nullptr) {
+        SegInitArgs sa{};
+        sa.begin = segin->begin; sa.end = segin->end; sa.num_segments = segin->num_segments; sa.offset_bytes = segin->offset_bytes;
+        sa.n = n; sa.segs = w.segs0; sa.max_segs = w.max_segs; sa.direct = segin->direct; sa.direct_small = segin->direct_small;
+        sa.ctr = ctr; sa.local_cap = C::LOCAL_CAP; sa.small_cap = C::SMALL_CAP; sa.end_bit = end_bit;
+        const int sgrid = (int)std::min<uint32_t>((segin->num_segments + 255) / 256, (uint32_t)sms * 8);
+        seg_init_kernel<<<std::max(sgrid, 1), 256, 0, s>>>(sa);
+        seg_clamp_kernel<<<1, 1, 0, s>>>(ctr, w.max_segs);
+      } else {
+        msb_init_kernel<<<1, 32, 0, s>>>(w.segs0, ctr, n);
+      }
+      scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(w.segs0, &ctr->num_segs[0], w.tile_base, &ctr->num_tiles[0], w.max_tiles, &ctr->error, C::TILE);
+      fill_descs_kernel<<<sms * 2, 256, 0, s>>>(w.segs0, w.tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], w.descs, C::TILE);
     }
-  }
-  if (fin_out) *fin_out = fin;
-  la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
-  if (segin != nullptr) {      // segments that fit on chip untouched: still in caller form, all of [begin_bit, end_bit) to sort
-    la.tw_in = twid;
-    la.items = segin->direct; la.num_items_ptr = &ctr->num_direct[0];
-    B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, segin->num_segments, s)));
-    la.items = segin->direct_small; la.num_items_ptr = &ctr->num_direct[1];
-    B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true>(la, segin->num_segments, s)));
+    for (int L = 0; L < levels; ++L) {
+      const int shift = std::max(begin_bit, end_bit - 8 * (L + 1));
+      const int nb = (end_bit - 8 * L) - shift;
+      const uint32_t mask = (1u << nb) - 1u;
+      Seg* cur = (L & 1) ? w.segs1 : w.segs0;
+      Seg* nxt = (L & 1) ? w.segs0 : w.segs1;
+      const int ib = in_buf(L), ob = out_buf(L);
+
+      { ProfScope prof("msb_sched", s); level_prep_kernel<<<sms * 2, 512, 0, s>>>(w.seg_hist, &ctr->num_segs[L]); }
+      TileHistArgs ha{};
+      ha.keys = bufk[ib]; ha.descs = w.descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
+      ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist;
+      ha.tile_cnt = w.tile_cnt;
+      ha.shift = shift; ha.mask = mask; ha.tw_in = (L == 0) ? twid : 0; ha.tw = tw;
+      ha.key_or = &ctr->key_or; ha.key_and = &ctr->key_and;
+#if B200_HIST_TICKET
+      ha.ticket = &ctr->part_ticket[L];
+#endif
+      const int hgrid = (int)std::min<uint32_t>(w.max_groups, (uint32_t)sms * 4);
+      if (L == 0 && probe == 2) {            // exact per-key OR / AND (the first round found a single level-0 bucket)
+        { ProfScope prof("tile_hist", s); tile_hist_kernel<K, false, true><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
+        { ProfScope prof("msb_sched", s); probe_eval_kernel<false><<<1, RADIX, 0, s>>>(ctr, w.seg_hist, shift, begin_bit, end_bit); }
+      } else {
+        { ProfScope prof("tile_hist", s); tile_hist_kernel<K, false, false><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
+        if (L == 0 && probe == 1) { ProfScope prof("msb_sched", s); probe_eval_kernel<true><<<1, RADIX, 0, s>>>(ctr, w.seg_hist, shift, begin_bit, end_bit); }
+      }
+      if (L == 0 && probe) {
+        B200_CHECK(cudaMemcpyAsync(probe_buffer(), &ctr->key_or, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        B200_CHECK(cudaEventRecord(probe_event(), s));
+      }
+      { ProfScope prof("msb_sched", s); group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(w.group_tail, w.group_flag, w.carry, &ctr->num_tiles[L]); }
+
+      ClassifyArgs ca{};
+      ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = w.seg_hist; ca.bins = w.bins;
+      ca.next_segs = nxt; ca.num_next_ptr = &ctr->num_segs[L + 1]; ca.max_segs = w.max_segs;
+      // buckets of this level: which on-chip algorithm.  More than 16 bits left -> one-shot counting sort; otherwise the unstable
+      // keys-only engine still prefers it for its large unmerged buckets (one cell per key value: half the shared-memory traffic of
+      // two LSD passes); merged runs, small buckets and the stable engine take the LSD kernels
+      int list = (shift - begin_bit > 16) ? ALGO_COUNT : ALGO_LSD;
+      const bool count_big = !ORDERED && VB == 0 && sizeof(K) == 4 && list == ALGO_LSD;
+      { static const char* e = getenv("B200SORT_LOCAL"); if (e) list = (e[0] == 'c') ? ALGO_COUNT : ALGO_LSD; }
+      const int big_list = count_big ? ALGO_COUNT : list;
+      ca.locals = w.locals[big_list]; ca.num_locals_ptr = &ctr->num_locals[big_list]; ca.max_locals = w.max_locals;
+      if (list == ALGO_LSD) { ca.locals_small = w.locals[3]; ca.num_small_ptr = &ctr->num_locals[2]; ca.small_cap = C::SMALL_CAP; }
+      if (count_big) { ca.locals_merged = w.locals[ALGO_LSD]; ca.num_merged_ptr = &ctr->num_locals[ALGO_LSD]; }   // merged runs need LSD passes
+      ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
+      ca.local_cap = C::LOCAL_CAP; ca.merge_cap = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP : C::MERGE_CAP;
+      ca.out_buf = (uint32_t)ob;
+      const int cgrid = (int)std::min<uint32_t>((w.max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
+      { ProfScope prof("msb_sched", s); classify_kernel<<<(L == 0 && segin == nullptr) ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca); }
+
+      ScatterArgs pa{};
+      pa.keys_in = bufk[ib]; pa.keys_out = bufk[ob]; pa.vals_in = bufv[ib]; pa.vals_out = bufv[ob];
+      pa.descs = w.descs; pa.num_tiles_ptr = &ctr->num_tiles[L];
+      pa.bins = w.bins; pa.tile_off = w.tile_off; pa.carry = w.carry; pa.tile_cnt = w.tile_cnt;
+      pa.shift = shift; pa.mask = mask; pa.tw_in = (L == 0) ? twid : 0; pa.tw_out = (shift == begin_bit) ? twid : 0; pa.tw = tw;
+      B200_CHECK((launch_scatter<K, VB, MODE_SEG, ORDERED>(pa, w.max_tiles, s)));
+
+      if (L + 1 < levels) {
+        ProfScope prof("msb_sched", s);
+        scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(nxt, &ctr->num_segs[L + 1], w.tile_base, &ctr->num_tiles[L + 1], w.max_tiles, &ctr->error, C::TILE);
+        fill_descs_kernel<<<sms * 2, 256, 0, s>>>(nxt, w.tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], w.descs, C::TILE);
+      }
+    }
+    if (fin_out) *fin_out = fin;
+    la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
+    if (segin != nullptr) {      // segments that fit on chip untouched: still in caller form, all of [begin_bit, end_bit) to sort
+      la.tw_in = twid;
+      la.items = segin->direct; la.num_items_ptr = &ctr->num_direct[0];
+      B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, segin->num_segments, s)));
+      la.items = segin->direct_small; la.num_items_ptr = &ctr->num_direct[1];
+      B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true>(la, segin->num_segments, s)));
+    }
+    la.tw_in = 0;
     la.items = w.locals[0]; la.num_items_ptr = &ctr->num_locals[0];
-  }
-  la.tw_in = 0;
-  B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
-  la.items = w.locals[3]; la.num_items_ptr = &ctr->num_locals[2];          // small buckets: the 256-thread configuration
-  B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true>(la, w.max_locals, s)));
-  if (end_bit - begin_bit > 24 || (!ORDERED && VB == 0 && sizeof(K) == 4)) {          // some level left more than 16 bits to its buckets / large keys-only buckets
-    la.items = w.locals[ALGO_COUNT]; la.num_items_ptr = &ctr->num_locals[ALGO_COUNT];
-    B200_CHECK((launch_local<K, VB, ALGO_COUNT, ORDERED>(la, w.max_locals, s)));
-    la.items = w.locals[2]; la.num_items_ptr = &ctr->num_overflow;       // buckets with overfull cells: LSD passes instead
     B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
+    la.items = w.locals[3]; la.num_items_ptr = &ctr->num_locals[2];          // small buckets: the 256-thread configuration
+    B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true>(la, w.max_locals, s)));
+    if (end_bit - begin_bit > 24 || (!ORDERED && VB == 0 && sizeof(K) == 4)) {          // some level left more than 16 bits to its buckets / large keys-only buckets
+      la.items = w.locals[ALGO_COUNT]; la.num_items_ptr = &ctr->num_locals[ALGO_COUNT];
+      B200_CHECK((launch_local<K, VB, ALGO_COUNT, ORDERED>(la, w.max_locals, s)));
+      la.items = w.locals[2]; la.num_items_ptr = &ctr->num_overflow;       // buckets with overfull cells: LSD passes instead
+      B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
+    }
+    if (!probe) break;
+    B200_CHECK(cudaEventSynchronize(probe_event()));
+    const unsigned long long* hp = probe_buffer();
+    if (probe == 1 && (hp[2] & 0xFFFFFFFFull) != 0) { probe = 2; continue; }      // one level-0 bucket: look at the lower bits too
+    probe = 0;
+    unsigned long long diff = hp[0] ^ hp[1];                                  // bits on which the keys differ
+    diff &= (end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1ull)) & ~((1ull << begin_bit) - 1ull);
+    int new_end = begin_bit;
+    while (new_end < end_bit && (diff >> new_end) != 0) ++new_end;           // highest differing bit + 1
+    if (new_end >= end_bit) break;                                            // the optimistic sort stands
+    // the enqueued sort found its lists emptied (probe_eval_kernel): sort again on the narrower window
+    end_bit = new_end;
+    levels = (end_bit - begin_bit + 7) / 8;
+    if (fin_in < 0) fin = levels & 1;
+    if (levels == 0) {                // all keys equal on the sorted bits: the input order is the (stable) answer
+      if (fin_out) *fin_out = fin;
+      if (fin != 0) {
+        B200_CHECK(cudaMemcpyAsync(bufk[fin], bufk[0], n * sizeof(K), cudaMemcpyDeviceToDevice, s));
+        if (VB) B200_CHECK(cudaMemcpyAsync(bufv[fin], bufv[0], n * sizeof(V), cudaMemcpyDeviceToDevice, s));
+      }
+      return cudaSuccess;
+    }
   }
   return cudaGetLastError();
 }
