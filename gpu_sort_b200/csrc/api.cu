@@ -127,7 +127,7 @@ int sort_host(bool msb, const void* hk, const void* hv, uint64_t n, void* hko, v
 
 extern "C" {
 
-int b200_version(void) { return 101; }
+int b200_version(void) { return 102; }
 
 int b200_prof_enable(int enable) {
   std::lock_guard<std::mutex> lock(g_prof_mu);

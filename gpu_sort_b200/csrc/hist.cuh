@@ -106,6 +106,7 @@ struct TileHistArgs {
 
 template <typename K, bool RANGE, bool PROBE>
 __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_constant__ TileHistArgs a) {
+  pdl_wait();
   __shared__ uint32_t sh[RADIX];
   const K* __restrict__ keys = reinterpret_cast<const K*>(a.keys);
   const uint32_t num_tiles = *a.num_tiles_ptr;
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
 constexpr int CARRY_WARPS = 32;
 static __global__ void __launch_bounds__(CARRY_WARPS * 32) group_carry_kernel(const uint32_t* group_tail, const uint32_t* group_flag, uint32_t* carry,
                                                                               const uint32_t* num_tiles_ptr) {
+  pdl_wait();
   __shared__ uint32_t p_sum[CARRY_WARPS][32];
   __shared__ uint32_t p_flag[CARRY_WARPS];
   const uint32_t num_groups = (*num_tiles_ptr + HIST_GROUP - 1) / HIST_GROUP;

@@ -27,6 +27,7 @@ struct MsbCounters {            // one small zero-initialised block in the works
 };
 
 static __global__ void msb_init_kernel(Seg* segs, MsbCounters* c, uint64_t n) {
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     segs[0].off = 0; segs[0].cnt = n;
     c->num_segs[0] = 1;
@@ -49,6 +50,7 @@ struct SegInitArgs {
   int end_bit;
 };
 static __global__ void __launch_bounds__(256) seg_init_kernel(const __grid_constant__ SegInitArgs a) {
+  pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.ctr->key_or = 0ull; a.ctr->key_and = ~0ull; }
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.num_segments; i += gridDim.x * blockDim.x) {
     long long b, e;
@@ -71,6 +73,7 @@ static __global__ void __launch_bounds__(256) seg_init_kernel(const __grid_const
 }
 
 static __global__ void seg_clamp_kernel(MsbCounters* c, uint32_t max_segs) {
+  pdl_wait();
   if (c->num_segs[0] > max_segs) c->num_segs[0] = 0;      // overlapping segments: the error flag is already up, nothing is sorted
 }
 
@@ -93,6 +96,7 @@ struct ClassifyArgs {
 constexpr int CLS_WARPS = 4;
 
 static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const __grid_constant__ ClassifyArgs a) {
+  pdl_wait();
   __shared__ uint32_t s_cnt[CLS_WARPS][RADIX];
   __shared__ uint64_t s_off[CLS_WARPS][RADIX];
   __shared__ LocalItem s_loc[CLS_WARPS][RADIX];
@@ -188,6 +192,7 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
 constexpr int SCAN_THREADS = 1024;
 static __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const Seg* segs, const uint32_t* num_segs_ptr, uint32_t* tile_base,
                                                                    uint32_t* num_tiles_ptr, uint32_t max_tiles, uint32_t* error, int tile) {
+  pdl_wait();
   __shared__ uint32_t s_w[32];
   const uint32_t ns = min(*num_segs_ptr, 0x7fffffffu);
   const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
@@ -228,6 +233,7 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const S
 
 static __global__ void fill_descs_kernel(const Seg* segs, const uint32_t* tile_base, const uint32_t* num_segs_ptr, const uint32_t* num_tiles_ptr,
                                          TileDesc* descs, int tile) {
+  pdl_wait();
   const uint32_t ns = *num_segs_ptr, nt = *num_tiles_ptr;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = ns;           // largest s with tile_base[s] <= t

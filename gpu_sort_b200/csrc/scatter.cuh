@@ -508,6 +508,7 @@ struct FastSmem {
 
 template <typename K, int VB, int THREADS, int IPT, int OCC>
 __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid_constant__ ScatterArgs a) {
+  pdl_wait();
   using SM = FastSmem<K, VB, THREADS, IPT>;
   using V = typename SM::V;
   constexpr int TILE = SM::TILE;
@@ -719,6 +720,7 @@ struct StableFastSmem {
 
 template <typename K, int VB, int THREADS, int IPT, int OCC>
 __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const __grid_constant__ ScatterArgs a) {
+  pdl_wait();
   using SM = StableFastSmem<K, VB, THREADS, IPT>;
   using V = typename SM::V;
   constexpr int TILE = SM::TILE, WARPS = SM::WARPS;

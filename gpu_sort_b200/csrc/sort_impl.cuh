@@ -10,6 +10,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdlib>
+#include <utility>
 #include "hist.cuh"
 #include "local_sort.cuh"
 #include "msb_sched.cuh"
@@ -24,6 +25,23 @@ inline int num_sms() {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   return sms;
+}
+
+// One launch of the sort's kernel chain: ordinary, or (B200_PDL) with programmatic stream serialisation.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+#if B200_PDL
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+#else
+  kernel<<<grid, block, smem, s>>>(std::forward<Args>(args)...);
+  return cudaSuccess;
+#endif
 }
 
 template <typename K, int VB>
@@ -88,7 +106,7 @@ inline cudaError_t launch_scatter_fast(const ScatterArgs& a, uint32_t tiles_hint
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
   ProfScope prof("scatter", s);
-  kernel<<<g, C::THREADS, smem, s>>>(a);
+  launch_k(kernel, g, C::THREADS, smem, s, a);
   return cudaGetLastError();
 }
 
@@ -102,7 +120,7 @@ inline cudaError_t launch_scatter_stable_fast(const ScatterArgs& a, uint32_t til
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
   ProfScope prof("scatter_stable", s);
-  kernel<<<g, C::THREADS, smem, s>>>(a);
+  launch_k(kernel, g, C::THREADS, smem, s, a);
   return cudaGetLastError();
 }
 
@@ -134,17 +152,19 @@ inline cudaError_t launch_local(const LocalArgs& a, uint32_t items_hint, cudaStr
   if (!grid) B200_CHECK(persistent_grid(kernel, THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
   ProfScope prof(ALGO == ALGO_LSD ? (SMALL ? "local_sort_lsd_small" : "local_sort_lsd") : "local_sort_count", s);
-  kernel<<<g, THREADS, smem, s>>>(a);
+  launch_k(kernel, g, THREADS, smem, s, a);
   return cudaGetLastError();
 }
 
 // Tiny helper kernels --------------------------------------------------------------------------------------------
 static __global__ void single_item_kernel(LocalItem* item, uint32_t* num_items, uint32_t cnt, int nbits) {
+  pdl_wait();
   LocalItem it; it.off = 0; it.cnt = cnt; it.nbits = (uint16_t)nbits; it.src = 0;
   *item = it; *num_items = 1;
 }
 // Zeroes the rows of the per-level arrays that the level will actually use.
 static __global__ void level_prep_kernel(uint32_t* seg_hist, const uint32_t* num_segs_ptr) {
+  pdl_wait();
   const uint64_t nh = (uint64_t)*num_segs_ptr * RADIX / 4;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint4 z = make_uint4(0, 0, 0, 0);
@@ -222,6 +242,7 @@ inline cudaEvent_t probe_event() {
 //   bits: key_or = key_and = 0 and probe_single = 1 ask the host for a round with the exact per-key OR / AND.
 template <bool FROM_HIST>
 static __global__ void __launch_bounds__(RADIX) probe_eval_kernel(MsbCounters* c, const uint32_t* seg_hist, int shift0, int begin_bit, int end_bit) {
+  pdl_wait();
   __shared__ uint32_t s_or, s_and, s_cnt;
   if (FROM_HIST) {
     if (threadIdx.x == 0) { s_or = 0; s_and = 0xFFFFFFFFu; s_cnt = 0; }
@@ -277,7 +298,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     if (fin_in < 0) fin = 0;
     if (fin_out) *fin_out = fin;
     la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
-    single_item_kernel<<<1, 1, 0, s>>>(w.locals[0], &ctr->num_locals[0], (uint32_t)n, end_bit);
+    launch_k(single_item_kernel, 1, 1, 0, s, w.locals[0], &ctr->num_locals[0], (uint32_t)n, end_bit);
     la.tw_in = twid;
     return launch_local<K, VB, ALGO_LSD, ORDERED>(la, 1, s);
   }
@@ -305,13 +326,13 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
         sa.n = n; sa.segs = w.segs0; sa.max_segs = w.max_segs; sa.direct = segin->direct; sa.direct_small = segin->direct_small;
         sa.ctr = ctr; sa.local_cap = C::LOCAL_CAP; sa.small_cap = C::SMALL_CAP; sa.end_bit = end_bit;
         const int sgrid = (int)std::min<uint32_t>((segin->num_segments + 255) / 256, (uint32_t)sms * 8);
-        seg_init_kernel<<<std::max(sgrid, 1), 256, 0, s>>>(sa);
-        seg_clamp_kernel<<<1, 1, 0, s>>>(ctr, w.max_segs);
+        launch_k(seg_init_kernel, std::max(sgrid, 1), 256, 0, s, sa);
+        launch_k(seg_clamp_kernel, 1, 1, 0, s, ctr, w.max_segs);
       } else {
-        msb_init_kernel<<<1, 32, 0, s>>>(w.segs0, ctr, n);
+        launch_k(msb_init_kernel, 1, 32, 0, s, w.segs0, ctr, n);
       }
-      scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(w.segs0, &ctr->num_segs[0], w.tile_base, &ctr->num_tiles[0], w.max_tiles, &ctr->error, C::TILE);
-      fill_descs_kernel<<<sms * 2, 256, 0, s>>>(w.segs0, w.tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], w.descs, C::TILE);
+      launch_k(scan_tiles_kernel, 1, SCAN_THREADS, 0, s, w.segs0, &ctr->num_segs[0], w.tile_base, &ctr->num_tiles[0], w.max_tiles, &ctr->error, C::TILE);
+      launch_k(fill_descs_kernel, sms * 2, 256, 0, s, w.segs0, w.tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], w.descs, C::TILE);
     }
     for (int L = 0; L < levels; ++L) {
       const int shift = std::max(begin_bit, end_bit - 8 * (L + 1));
@@ -321,7 +342,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
       Seg* nxt = (L & 1) ? w.segs0 : w.segs1;
       const int ib = in_buf(L), ob = out_buf(L);
 
-      { ProfScope prof("msb_sched", s); level_prep_kernel<<<sms * 2, 512, 0, s>>>(w.seg_hist, &ctr->num_segs[L]); }
+      { ProfScope prof("msb_sched", s); launch_k(level_prep_kernel, sms * 2, 512, 0, s, w.seg_hist, &ctr->num_segs[L]); }
       TileHistArgs ha{};
       ha.keys = bufk[ib]; ha.descs = w.descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
       ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist;
@@ -333,17 +354,17 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
 #endif
       const int hgrid = (int)std::min<uint32_t>(w.max_groups, (uint32_t)sms * 4);
       if (L == 0 && probe == 2) {            // exact per-key OR / AND (the first round found a single level-0 bucket)
-        { ProfScope prof("tile_hist", s); tile_hist_kernel<K, false, true><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
-        { ProfScope prof("msb_sched", s); probe_eval_kernel<false><<<1, RADIX, 0, s>>>(ctr, w.seg_hist, shift, begin_bit, end_bit); }
+        { ProfScope prof("tile_hist", s); launch_k(tile_hist_kernel<K, false, true>, hgrid, HIST_THREADS, 0, s, ha); }
+        { ProfScope prof("msb_sched", s); launch_k(probe_eval_kernel<false>, 1, RADIX, 0, s, ctr, w.seg_hist, shift, begin_bit, end_bit); }
       } else {
-        { ProfScope prof("tile_hist", s); tile_hist_kernel<K, false, false><<<hgrid, HIST_THREADS, 0, s>>>(ha); }
-        if (L == 0 && probe == 1) { ProfScope prof("msb_sched", s); probe_eval_kernel<true><<<1, RADIX, 0, s>>>(ctr, w.seg_hist, shift, begin_bit, end_bit); }
+        { ProfScope prof("tile_hist", s); launch_k(tile_hist_kernel<K, false, false>, hgrid, HIST_THREADS, 0, s, ha); }
+        if (L == 0 && probe == 1) { ProfScope prof("msb_sched", s); launch_k(probe_eval_kernel<true>, 1, RADIX, 0, s, ctr, w.seg_hist, shift, begin_bit, end_bit); }
       }
       if (L == 0 && probe) {
         B200_CHECK(cudaMemcpyAsync(probe_buffer(), &ctr->key_or, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         B200_CHECK(cudaEventRecord(probe_event(), s));
       }
-      { ProfScope prof("msb_sched", s); group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(w.group_tail, w.group_flag, w.carry, &ctr->num_tiles[L]); }
+      { ProfScope prof("msb_sched", s); launch_k(group_carry_kernel, RADIX / 32, CARRY_WARPS * 32, 0, s, w.group_tail, w.group_flag, w.carry, &ctr->num_tiles[L]); }
 
       ClassifyArgs ca{};
       ca.segs = cur; ca.num_segs_ptr = &ctr->num_segs[L]; ca.seg_hist = w.seg_hist; ca.bins = w.bins;
@@ -362,7 +383,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
       ca.local_cap = C::LOCAL_CAP; ca.merge_cap = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP : C::MERGE_CAP;
       ca.out_buf = (uint32_t)ob;
       const int cgrid = (int)std::min<uint32_t>((w.max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
-      { ProfScope prof("msb_sched", s); classify_kernel<<<(L == 0 && segin == nullptr) ? 1 : cgrid, CLS_WARPS * 32, 0, s>>>(ca); }
+      { ProfScope prof("msb_sched", s); launch_k(classify_kernel, (L == 0 && segin == nullptr) ? 1 : cgrid, CLS_WARPS * 32, 0, s, ca); }
 
       ScatterArgs pa{};
       pa.keys_in = bufk[ib]; pa.keys_out = bufk[ob]; pa.vals_in = bufv[ib]; pa.vals_out = bufv[ob];
@@ -373,8 +394,8 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
 
       if (L + 1 < levels) {
         ProfScope prof("msb_sched", s);
-        scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(nxt, &ctr->num_segs[L + 1], w.tile_base, &ctr->num_tiles[L + 1], w.max_tiles, &ctr->error, C::TILE);
-        fill_descs_kernel<<<sms * 2, 256, 0, s>>>(nxt, w.tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], w.descs, C::TILE);
+        launch_k(scan_tiles_kernel, 1, SCAN_THREADS, 0, s, nxt, &ctr->num_segs[L + 1], w.tile_base, &ctr->num_tiles[L + 1], w.max_tiles, &ctr->error, C::TILE);
+        launch_k(fill_descs_kernel, sms * 2, 256, 0, s, nxt, w.tile_base, &ctr->num_segs[L + 1], &ctr->num_tiles[L + 1], w.descs, C::TILE);
       }
     }
     if (fin_out) *fin_out = fin;
