@@ -21,6 +21,13 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// EXPERIMENTAL, off by default, NOT yet run on a GPU (written after round 1's GPU budget was spent):
+// B200_SEG_CONST=1 lets the MSD levels recognise a segment whose keys are all equal on the bits still to be sorted and
+// finish it by plain copies instead of scattering it at every remaining level (hot keys of duplicate-heavy inputs).
+#ifndef B200_SEG_CONST
+#define B200_SEG_CONST 0
+#endif
+
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 256;
 

@@ -102,12 +102,15 @@ struct TileHistArgs {
   const uint32_t* splitters; int num_parts;     // range mode: digit = #{ j < num_parts-1 : splitters[j] <= (key >> shift) }
   unsigned long long* key_or; unsigned long long* key_and;   // PROBE: OR / AND of all transformed keys are accumulated here
   uint32_t* ticket;                            // zeroed counter: groups are handed out dynamically (nullptr: round-robin)
+  unsigned long long* seg_or; unsigned long long* seg_and;   // SEGP: per-SEGMENT OR / AND of the keys (initialised to 0 / ~0)
 };
 
-template <typename K, bool RANGE, bool PROBE>
+template <typename K, bool RANGE, bool PROBE, bool SEGP = false>
 __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_constant__ TileHistArgs a) {
   pdl_wait();
   __shared__ uint32_t sh[RADIX];
+  __shared__ uint32_t s_sor[2], s_sand[2];     // SEGP: OR / AND of the current tile's keys (low, high word)
+  K t_or = (K)0, t_and = (K)~(K)0;             // SEGP: this thread's share of them
   const K* __restrict__ keys = reinterpret_cast<const K*>(a.keys);
   const uint32_t num_tiles = *a.num_tiles_ptr;
   const uint32_t num_groups = (num_tiles + HIST_GROUP - 1) / HIST_GROUP;
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
   auto count = [&](K k) {
     if (a.tw_in) k = (K)(k ^ (((K)((S)k >> (sizeof(K) * 8 - 1)) & fl) | sg) ^ fp);
     if (PROBE) { acc_or |= k; acc_and &= k; }
+    if (SEGP) { t_or |= k; t_and &= k; }
     uint32_t d;
     if (!RANGE) d = digit_of<K>(k, shift, mask);
     else d = range_part(rl, (uint32_t)(k >> shift), cshift);
@@ -140,6 +144,10 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
     for (uint32_t t = t0; t < t1; ++t) {
       const TileDesc td = a.descs[t];
       if (tid < RADIX) sh[tid] = 0;
+      if (SEGP) {
+        if (tid == 0) { s_sor[0] = 0; s_sor[1] = 0; s_sand[0] = 0xFFFFFFFFu; s_sand[1] = 0xFFFFFFFFu; }
+        t_or = (K)0; t_and = (K)~(K)0;
+      }
       __syncthreads();
       const uint32_t cnt = td.cnt;
       const K* p = keys + td.off;
@@ -168,7 +176,20 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
       if (tid < head) count(p[tid]);
       const uint32_t tail0 = head + nvec * VEC;
       if (tail0 + tid < cnt) count(p[tail0 + tid]);
+      if (SEGP) {          // one REDUX pair per warp and key word, then one shared-memory atomic pair per warp
+        const uint32_t o0 = __reduce_or_sync(0xffffffffu, (uint32_t)t_or), a0 = __reduce_and_sync(0xffffffffu, (uint32_t)t_and);
+        uint32_t o1 = 0, a1 = 0xFFFFFFFFu;
+        if (sizeof(K) == 8) {
+          o1 = __reduce_or_sync(0xffffffffu, (uint32_t)((unsigned long long)t_or >> 32));
+          a1 = __reduce_and_sync(0xffffffffu, (uint32_t)((unsigned long long)t_and >> 32));
+        }
+        if ((tid & 31u) == 0) { atomicOr(&s_sor[0], o0); atomicAnd(&s_sand[0], a0); if (sizeof(K) == 8) { atomicOr(&s_sor[1], o1); atomicAnd(&s_sand[1], a1); } }
+      }
       __syncthreads();
+      if (SEGP && tid == 0 && cnt != 0) {
+        atomicOr(&a.seg_or[td.seg], ((unsigned long long)s_sor[1] << 32) | s_sor[0]);
+        atomicAnd(&a.seg_and[td.seg], ((unsigned long long)s_sand[1] << 32) | s_sand[0]);
+      }
       if (tid < RADIX) {
         const uint32_t c = sh[tid];
         if (td.tile_in_seg == 0) {                       // a segment starts here: close the previous one

@@ -91,6 +91,11 @@ struct ClassifyArgs {
   int last;                     // no bits remain below this digit: every sub-bucket is final after the scatter
   uint32_t local_cap, merge_cap;
   uint32_t out_buf;             // ping-pong buffer the level scatters into
+  // B200_SEG_CONST: per-segment OR / AND of the keys (nullptr: off) -- a segment whose keys agree on every bit still to be
+  // sorted, [begin_bit, shift + nb), is finished by copy-through items (nbits = begin_bit: zero on-chip passes) in the LSD list
+  const unsigned long long* seg_or; const unsigned long long* seg_and;
+  LocalItem* locals_copy; uint32_t* num_copy_ptr;
+  int begin_bit;
 };
 
 constexpr int CLS_WARPS = 4;
@@ -125,6 +130,31 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
     }
     __syncwarp();
     if (a.last) continue;             // last digit: every sub-bucket is final after the scatter
+#if B200_SEG_CONST
+    if (a.seg_or != nullptr) {
+      const int top = a.shift + a.nb;
+      unsigned long long diff = a.seg_or[s] ^ a.seg_and[s];
+      diff &= (top >= 64 ? ~0ull : ((1ull << top) - 1ull)) & ~((1ull << a.begin_bit) - 1ull);
+      if (diff == 0ull) {
+        // all keys of the segment are equal where it matters: this level's scatter copies it unchanged into out_buf (one digit);
+        // nothing below needs sorting -- hand it to the on-chip kernel in capacity-sized chunks that just copy it to the final buffer
+        const uint32_t chunks = (uint32_t)((sg.cnt + a.local_cap - 1) / a.local_cap);
+        uint32_t cbase = 0;
+        if (lane == 0) cbase = atomicAdd(a.num_copy_ptr, chunks);
+        cbase = __shfl_sync(0xffffffffu, cbase, 0);
+        if (cbase + chunks > a.max_locals) { if (lane == 0) atomicOr(a.error, (uint32_t)ERR_LOCAL_OVERFLOW); continue; }
+        for (uint32_t i = lane; i < chunks; i += 32) {
+          LocalItem it; it.off = sg.off + (uint64_t)i * a.local_cap;
+          const uint64_t rest = sg.cnt - (uint64_t)i * a.local_cap;
+          it.cnt = (uint32_t)(rest < (uint64_t)a.local_cap ? rest : (uint64_t)a.local_cap);
+          it.nbits = (uint16_t)a.begin_bit; it.src = (uint16_t)a.out_buf;
+          a.locals_copy[cbase + i] = it;
+        }
+        __syncwarp();
+        continue;
+      }
+    }
+#endif
     // classify + merge, serial over the 256 digits (lane 0), staged in shared memory
     uint32_t nloc = 0, nseg = 0, nsml = 0, nmrg = 0;     // big items fill s_loc[w] from the front, small ones from the back;
     LocalItem* s_mrg = reinterpret_cast<LocalItem*>(&s_seg[w][0]);   // merged runs share s_seg[w] with the segments, from the back

@@ -163,12 +163,14 @@ static __global__ void single_item_kernel(LocalItem* item, uint32_t* num_items, 
   *item = it; *num_items = 1;
 }
 // Zeroes the rows of the per-level arrays that the level will actually use.
-static __global__ void level_prep_kernel(uint32_t* seg_hist, const uint32_t* num_segs_ptr) {
+static __global__ void level_prep_kernel(uint32_t* seg_hist, const uint32_t* num_segs_ptr, unsigned long long* seg_or, unsigned long long* seg_and) {
   pdl_wait();
   const uint64_t nh = (uint64_t)*num_segs_ptr * RADIX / 4;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint4 z = make_uint4(0, 0, 0, 0);
   for (uint64_t i = t; i < nh; i += stride) reinterpret_cast<uint4*>(seg_hist)[i] = z;
+  if (seg_or != nullptr)
+    for (uint64_t i = t; i < (uint64_t)*num_segs_ptr; i += stride) { seg_or[i] = 0ull; seg_and[i] = ~0ull; }
 }
 
 struct Carver {      // sub-allocates the caller's temporary storage, 256-byte aligned
@@ -197,6 +199,7 @@ struct MsdWorkspace {
   MsbCounters* ctr; Seg* segs0; Seg* segs1; uint32_t* tile_base; TileDesc* descs; uint32_t* seg_hist; uint64_t* bins;
   uint32_t* tile_off; uint16_t* tile_cnt; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[4];   // LSD list, counting list, overflow, small-bucket LSD list
   uint32_t max_segs, max_tiles, max_locals, max_groups;
+  unsigned long long* seg_or; unsigned long long* seg_and;      // B200_SEG_CONST: per-segment OR / AND of the keys
 };
 
 template <typename K, int VB>
@@ -220,6 +223,10 @@ inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
   w.group_flag = cv.take<uint32_t>(w.max_groups);
   w.carry = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
   for (int i = 0; i < 4; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
+#if B200_SEG_CONST
+  w.seg_or = cv.take<unsigned long long>(w.max_segs);
+  w.seg_and = cv.take<unsigned long long>(w.max_segs);
+#endif
 }
 
 // Pinned landing zone for the key-range probe: key_or, key_and, {probe_single, -} (one per host thread).
@@ -341,8 +348,11 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
       Seg* cur = (L & 1) ? w.segs1 : w.segs0;
       Seg* nxt = (L & 1) ? w.segs0 : w.segs1;
       const int ib = in_buf(L), ob = out_buf(L);
+      // B200_SEG_CONST (experimental): from level 1 on the histogram also keeps a per-segment OR / AND of the keys; level 0 is one
+      // segment, covered by the key-range probe; the last level's buckets are final after its scatter anyway
+      const bool segp = B200_SEG_CONST != 0 && L >= 1 && L + 1 < levels && w.seg_or != nullptr;
 
-      { ProfScope prof("msb_sched", s); launch_k(level_prep_kernel, sms * 2, 512, 0, s, w.seg_hist, &ctr->num_segs[L]); }
+      { ProfScope prof("msb_sched", s); launch_k(level_prep_kernel, sms * 2, 512, 0, s, w.seg_hist, &ctr->num_segs[L], segp ? w.seg_or : nullptr, segp ? w.seg_and : nullptr); }
       TileHistArgs ha{};
       ha.keys = bufk[ib]; ha.descs = w.descs; ha.num_tiles_ptr = &ctr->num_tiles[L];
       ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist;
@@ -356,6 +366,9 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
       if (L == 0 && probe == 2) {            // exact per-key OR / AND (the first round found a single level-0 bucket)
         { ProfScope prof("tile_hist", s); launch_k(tile_hist_kernel<K, false, true>, hgrid, HIST_THREADS, 0, s, ha); }
         { ProfScope prof("msb_sched", s); launch_k(probe_eval_kernel<false>, 1, RADIX, 0, s, ctr, w.seg_hist, shift, begin_bit, end_bit); }
+      } else if (segp) {
+        ha.seg_or = w.seg_or; ha.seg_and = w.seg_and;
+        { ProfScope prof("tile_hist", s); launch_k(tile_hist_kernel<K, false, false, B200_SEG_CONST != 0>, hgrid, HIST_THREADS, 0, s, ha); }
       } else {
         { ProfScope prof("tile_hist", s); launch_k(tile_hist_kernel<K, false, false>, hgrid, HIST_THREADS, 0, s, ha); }
         if (L == 0 && probe == 1) { ProfScope prof("msb_sched", s); launch_k(probe_eval_kernel<true>, 1, RADIX, 0, s, ctr, w.seg_hist, shift, begin_bit, end_bit); }
@@ -382,6 +395,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
       ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
       ca.local_cap = C::LOCAL_CAP; ca.merge_cap = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP : C::MERGE_CAP;
       ca.out_buf = (uint32_t)ob;
+      if (segp) { ca.seg_or = w.seg_or; ca.seg_and = w.seg_and; ca.locals_copy = w.locals[ALGO_LSD]; ca.num_copy_ptr = &ctr->num_locals[ALGO_LSD]; ca.begin_bit = begin_bit; }
       const int cgrid = (int)std::min<uint32_t>((w.max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
       { ProfScope prof("msb_sched", s); launch_k(classify_kernel, (L == 0 && segin == nullptr) ? 1 : cgrid, CLS_WARPS * 32, 0, s, ca); }
 
