@@ -268,7 +268,7 @@ static __global__ void __launch_bounds__(RADIX) probe_eval_kernel(MsbCounters* c
   diff &= (end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1ull)) & ~((1ull << begin_bit) - 1ull);
   if (end_bit > begin_bit && ((diff >> (end_bit - 1)) & 1ull) == 0ull) { c->num_tiles[0] = 0; c->num_segs[0] = 0; }
 }
-constexpr uint64_t PROBE_MIN_ITEMS = 1ull << 22;     // below this the extra stream synchronisation costs more than it can save
+constexpr uint64_t PROBE_MIN_ITEMS = 1ull << 22;     // below this the read-back and the host's event wait cost more than the probe can save
 
 // Caller-defined segments (segmented sort): offsets on the device, plus two work lists for the segments that fit on chip as they are.
 struct SegInput {

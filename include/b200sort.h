@@ -9,9 +9,12 @@
  * Conventions
  *   - plain pointers and sizes only; every function returns a cudaError_t value (0 = cudaSuccess) and never exits
  *     (the reference calls exit(-1), msb/src/sort/gpu_radix_sort.h:397-400);
- *   - all device work is enqueued on `stream`; no host<->device synchronisation and no allocation happens inside a
- *     call when the caller supplies the temporary storage (the reference MSB blocks the host several times per
- *     pass and cudaMallocs inside the call, gpu_radix_sort.h:224-228,387,489-491);
+ *   - all device work is enqueued on `stream`; no allocation happens inside a call when the caller supplies the
+ *     temporary storage, and the host never waits in the middle of a sort (the reference MSB blocks the host several
+ *     times per pass and cudaMallocs inside the call, gpu_radix_sort.h:224-228,387,489-491).  One exception, for
+ *     num_items >= 2^22 outside CUDA-graph capture: after enqueuing the whole sort the call waits for a 24-byte
+ *     read-back taken behind the first histogram (key-range probe), i.e. it returns while the
+ *     device is still sorting but not before the first pass over the keys has finished;
  *   - item counts are 64-bit (reference: int / unsigned int, device_radix_sort.cuh:154, gpu_radix_sort.h:190);
  *   - key order is the reference's bit-transform order (cub::Traits<T>::TwiddleIn, lsb/cub/cub/util_type.cuh:966-1089):
  *     unsigned as is, signed with the sign bit flipped, floating point as -NaN < -inf < ... < -0.0 < +0.0 < ... < +inf < +NaN.
