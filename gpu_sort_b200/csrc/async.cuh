@@ -39,6 +39,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // orders earlier generic-proxy accesses to shared memory before later async-proxy (bulk copy) writes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Shared-memory accesses through explicit 32-bit shared-window addresses.  The hot per-key paths keep their table bases in
+// registers and add the element offset themselves: left to the compiler, the base of the dynamic shared-memory window was
+// re-derived (S2R SR_CgaCtaId + LEA) for every key under register pressure (profiles/r02_rank_v2.txt).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_or(uint32_t addr, uint32_t v) { uint32_t o; asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory"); return o; }
+template <typename T> __device__ __forceinline__ void sts_t(uint32_t addr, T v) { if (sizeof(T) == 4) sts_u32(addr, (uint32_t)v); else sts_u64(addr, (uint64_t)v); }
+
 // A [off, off+cnt) element window of a global array as a 16-byte aligned byte range for bulk_g2s:
 // the copy starts `skew` elements before the window and may cover up to 15 bytes after it (same 16-byte granule as
 // the last element, hence inside the same allocation granule as valid data).

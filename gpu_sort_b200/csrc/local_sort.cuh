@@ -29,7 +29,9 @@ struct LocalArgs {
   void* keys[3]; void* vals[3];          // the ping-pong buffers (LocalItem::src indexes them)
   void* keys_final; void* vals_final;
   const LocalItem* items; const uint32_t* num_items_ptr;
-  LocalItem* overflow; uint32_t* num_overflow_ptr;     // ALGO_COUNT: buckets it could not take
+  uint32_t max_items;                    // capacity of every work list (a count above it means the list overflowed: the error flag is up)
+  LocalItem* overflow; uint32_t* num_overflow_ptr;     // ALGO_COUNT / bitmap sort: buckets they could not take
+  uint32_t* error_ptr;                   // MsbCounters::error
   int tw_in;                             // keys still in caller form (single-tile sorts)
   int tw_out;
   int begin_bit;                         // lowest bit to sort (0 for MSB items)
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const unsigned tid = threadIdx.x;
-  const uint32_t num_items = *a.num_items_ptr;
+  const uint32_t num_items = min(*a.num_items_ptr, a.max_items);
   K* __restrict__ keys_out = reinterpret_cast<K*>(a.keys_final);
   V* __restrict__ vals_out = reinterpret_cast<V*>(a.vals_final);
 
@@ -477,7 +479,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 
       aoff = vec ? (uint32_t)((reinterpret_cast<uintptr_t>(keys_out + it.off) & 15u) / sizeof(K)) : 0u;
       sorted = count_sort_item<K, VB, THREADS, IPT, STABLE>(sk, sv, sm.origin, skew, vskew, cnt, lo, hi, a.tw_in != 0, a.tw,
                                                              *reinterpret_cast<CountSmem<THREADS, CountBits<K, VB>::value>*>(&sm.rank), aoff);
-      if (!sorted && tid == 0) a.overflow[atomicAdd(a.num_overflow_ptr, 1u)] = it;
+      if (!sorted && tid == 0) {
+        const uint32_t o = atomicAdd(a.num_overflow_ptr, 1u);
+        if (o < a.max_items) a.overflow[o] = it; else atomicOr(a.error_ptr, 2u);
+      }
     } else {
       lsd_sort_item<K, VB, THREADS, IPT, STABLE>(sk, sv, skew, vskew, cnt, lo, hi, a.tw_in != 0, a.tw, *reinterpret_cast<LsdSmem<THREADS>*>(&sm.rank));
     }

@@ -20,7 +20,7 @@ struct MsbCounters {            // one small zero-initialised block in the works
   uint32_t num_locals[3];       // work lists of the on-chip sorts: ALGO_LSD, ALGO_COUNT, small ALGO_LSD buckets
   uint32_t num_overflow;        // buckets the counting sort handed back
   uint32_t error;
-  uint32_t pad;
+  uint32_t num_bitmap;          // work list of the presence-bitmap sort (large keys-only buckets with <= 16 bits left)
   uint32_t num_direct[2];       // segmented sort: caller segments that fit on chip as they are (large / small on-chip configuration)
   unsigned long long key_or, key_and;     // OR / AND of all transformed keys (level-0 histogram): bits where they agree are constant
   uint32_t probe_single, pad2;            // (read back together with key_or / key_and) the level-0 histogram has one non-empty bucket

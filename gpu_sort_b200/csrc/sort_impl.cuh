@@ -13,6 +13,8 @@
 #include <utility>
 #include "hist.cuh"
 #include "local_sort.cuh"
+#include "local_bitmap.cuh"
+#include "local_rank.cuh"
 #include "msb_sched.cuh"
 #include "scatter.cuh"
 #include "sort_api.h"
@@ -156,6 +158,56 @@ inline cudaError_t launch_local(const LocalArgs& a, uint32_t items_hint, cudaStr
   return cudaGetLastError();
 }
 
+// Keys-only buckets with <= 16 undecided bits where the sort covers the whole key: presence-bitmap sort (local_bitmap.cuh).
+#ifndef B200_BITMAP_THREADS
+#define B200_BITMAP_THREADS 256
+#endif
+#ifndef B200_BITMAP_OCC
+#define B200_BITMAP_OCC 4
+#endif
+template <typename K, int VB>
+inline cudaError_t launch_bitmap(const LocalArgs& a, uint32_t items_hint, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  auto kernel = bitmap_sort_kernel<K, B200_BITMAP_THREADS, C::LOCAL_CAP, B200_BITMAP_OCC>;
+  constexpr size_t smem = sizeof(BitmapSmem<K, B200_BITMAP_THREADS, C::LOCAL_CAP>);
+  static int grid = 0;
+  if (!grid) B200_CHECK(persistent_grid(kernel, B200_BITMAP_THREADS, smem, &grid));
+  const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
+  ProfScope prof("local_sort_bitmap", s);
+  launch_k(kernel, g, B200_BITMAP_THREADS, smem, s, a);
+  return cudaGetLastError();
+}
+
+// 4-byte keys, buckets with <= 16 undecided bits: one-shot rank by presence bits (local_rank.cuh).
+#ifndef B200_RANK_THREADS
+#define B200_RANK_THREADS 512      // pairs
+#endif
+#ifndef B200_RANK_THREADS0
+#define B200_RANK_THREADS0 256     // keys-only
+#endif
+#ifndef B200_RANK_OCC
+#define B200_RANK_OCC 0            // 0: as many CTAs per SM as shared memory and the thread limit allow
+#endif
+#ifndef B200_RANK_OCC0
+#define B200_RANK_OCC0 0
+#endif
+template <typename K, int VB, bool STABLE>
+inline cudaError_t launch_rank(const LocalArgs& a, uint32_t items_hint, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  constexpr int THREADS = VB ? B200_RANK_THREADS : B200_RANK_THREADS0, IPT = C::LOCAL_CAP / THREADS;
+  static_assert(THREADS * IPT == C::LOCAL_CAP, "the rank kernel's capacity is the on-chip capacity of the configuration");
+  constexpr size_t smem = sizeof(RankSmem<K, VB, THREADS, IPT, STABLE>);
+  constexpr int OCC_SET = VB ? B200_RANK_OCC : B200_RANK_OCC0;
+  constexpr int OCC = OCC_SET ? OCC_SET : (int)std::min<size_t>((227 * 1024) / (smem + 1024), 2048 / THREADS);
+  auto kernel = rank_sort_kernel<K, VB, THREADS, IPT, OCC, STABLE>;
+  static int grid = 0;
+  if (!grid) B200_CHECK(persistent_grid(kernel, THREADS, smem, &grid));
+  const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
+  ProfScope prof("local_sort_rank", s);
+  launch_k(kernel, g, THREADS, smem, s, a);
+  return cudaGetLastError();
+}
+
 // Tiny helper kernels --------------------------------------------------------------------------------------------
 static __global__ void single_item_kernel(LocalItem* item, uint32_t* num_items, uint32_t cnt, int nbits) {
   pdl_wait();
@@ -197,7 +249,7 @@ struct Carver {      // sub-allocates the caller's temporary storage, 256-byte a
 // ===============================================================================================================
 struct MsdWorkspace {
   MsbCounters* ctr; Seg* segs0; Seg* segs1; uint32_t* tile_base; TileDesc* descs; uint32_t* seg_hist; uint64_t* bins;
-  uint32_t* tile_off; uint16_t* tile_cnt; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[4];   // LSD list, counting list, overflow, small-bucket LSD list
+  uint32_t* tile_off; uint16_t* tile_cnt; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[5];   // LSD list, counting list, overflow, small-bucket LSD list, bitmap list
   uint32_t max_segs, max_tiles, max_locals, max_groups;
   unsigned long long* seg_or; unsigned long long* seg_and;      // B200_SEG_CONST: per-segment OR / AND of the keys
 };
@@ -222,7 +274,7 @@ inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
   w.group_tail = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
   w.group_flag = cv.take<uint32_t>(w.max_groups);
   w.carry = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
-  for (int i = 0; i < 4; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
+  for (int i = 0; i < 5; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
 #if B200_SEG_CONST
   w.seg_or = cv.take<unsigned long long>(w.max_segs);
   w.seg_and = cv.take<unsigned long long>(w.max_segs);
@@ -299,6 +351,15 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   for (int i = 0; i < 3; ++i) { la.keys[i] = bufk[i < nbuf ? i : 0]; la.vals[i] = bufv[i < nbuf ? i : 0]; }
   la.items = w.locals[0]; la.num_items_ptr = &ctr->num_locals[0];
   la.overflow = w.locals[2]; la.num_overflow_ptr = &ctr->num_overflow;
+  la.max_items = w.max_locals; la.error_ptr = &ctr->error;
+  // the sort covers the whole key: buckets whose undecided bits are equal hold equal keys, so the on-chip sort may rebuild keys from cells
+  const bool whole_key = begin_bit == 0 && end_bit == (int)sizeof(K) * 8;
+  // which kernel finishes the large buckets with <= 16 bits left (measurement switch B200SORT_LOCAL=rank|bitmap|old)
+  bool use_rank = sizeof(K) == 4;
+  bool use_bitmap = false;
+  { static const char* e = getenv("B200SORT_LOCAL");
+    if (e && e[0] == 'b') { use_rank = false; use_bitmap = !ORDERED && VB == 0 && sizeof(K) == 4 && whole_key; }
+    if (e && e[0] == 'o') use_rank = false; }
   la.tw_out = twid; la.begin_bit = begin_bit; la.tw = tw;
 
   if (segin == nullptr && n <= (uint64_t)C::LOCAL_CAP) {     // fits one CTA: a single on-chip sort straight into the final buffer
@@ -387,11 +448,12 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
       // two LSD passes); merged runs, small buckets and the stable engine take the LSD kernels
       int list = (shift - begin_bit > 16) ? ALGO_COUNT : ALGO_LSD;
       const bool count_big = !ORDERED && VB == 0 && sizeof(K) == 4 && list == ALGO_LSD;
-      { static const char* e = getenv("B200SORT_LOCAL"); if (e) list = (e[0] == 'c') ? ALGO_COUNT : ALGO_LSD; }
       const int big_list = count_big ? ALGO_COUNT : list;
+      const bool big_special = list == ALGO_LSD && (use_rank || (count_big && use_bitmap));     // large unmerged buckets get their own list
       ca.locals = w.locals[big_list]; ca.num_locals_ptr = &ctr->num_locals[big_list]; ca.max_locals = w.max_locals;
+      if (big_special) { ca.locals = w.locals[4]; ca.num_locals_ptr = &ctr->num_bitmap; }
       if (list == ALGO_LSD) { ca.locals_small = w.locals[3]; ca.num_small_ptr = &ctr->num_locals[2]; ca.small_cap = C::SMALL_CAP; }
-      if (count_big) { ca.locals_merged = w.locals[ALGO_LSD]; ca.num_merged_ptr = &ctr->num_locals[ALGO_LSD]; }   // merged runs need LSD passes
+      if (count_big || big_special) { ca.locals_merged = w.locals[ALGO_LSD]; ca.num_merged_ptr = &ctr->num_locals[ALGO_LSD]; }   // merged runs need LSD passes
       ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
       ca.local_cap = C::LOCAL_CAP; ca.merge_cap = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP : C::MERGE_CAP;
       ca.out_buf = (uint32_t)ob;
@@ -415,21 +477,29 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
     if (fin_out) *fin_out = fin;
     la.keys_final = bufk[fin]; la.vals_final = bufv[fin];
     if (segin != nullptr) {      // segments that fit on chip untouched: still in caller form, all of [begin_bit, end_bit) to sort
-      la.tw_in = twid;
+      la.tw_in = twid; la.max_items = segin->num_segments;
       la.items = segin->direct; la.num_items_ptr = &ctr->num_direct[0];
       B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, segin->num_segments, s)));
       la.items = segin->direct_small; la.num_items_ptr = &ctr->num_direct[1];
       B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true>(la, segin->num_segments, s)));
     }
-    la.tw_in = 0;
+    la.tw_in = 0; la.max_items = w.max_locals;
     la.items = w.locals[0]; la.num_items_ptr = &ctr->num_locals[0];
     B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
     la.items = w.locals[3]; la.num_items_ptr = &ctr->num_locals[2];          // small buckets: the 256-thread configuration
     B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true>(la, w.max_locals, s)));
-    if (end_bit - begin_bit > 24 || (!ORDERED && VB == 0 && sizeof(K) == 4)) {          // some level left more than 16 bits to its buckets / large keys-only buckets
-      la.items = w.locals[ALGO_COUNT]; la.num_items_ptr = &ctr->num_locals[ALGO_COUNT];
-      B200_CHECK((launch_local<K, VB, ALGO_COUNT, ORDERED>(la, w.max_locals, s)));
-      la.items = w.locals[2]; la.num_items_ptr = &ctr->num_overflow;       // buckets with overfull cells: LSD passes instead
+    {
+      la.items = w.locals[ALGO_COUNT]; la.num_items_ptr = &ctr->num_locals[ALGO_COUNT];      // more than 16 bits left (or the legacy exact-cell mode)
+      if (end_bit - begin_bit > 24 || (!ORDERED && VB == 0 && sizeof(K) == 4 && !use_rank && !use_bitmap))
+        B200_CHECK((launch_local<K, VB, ALGO_COUNT, ORDERED>(la, w.max_locals, s)));
+      la.items = w.locals[4]; la.num_items_ptr = &ctr->num_bitmap;                            // large buckets with <= 16 bits left
+      if constexpr (sizeof(K) == 4) {
+        if (use_rank) B200_CHECK((launch_rank<K, VB, ORDERED>(la, w.max_locals, s)));
+      }
+      if constexpr (!ORDERED && VB == 0 && sizeof(K) == 4) {
+        if (use_bitmap) B200_CHECK((launch_bitmap<K, VB>(la, w.max_locals, s)));
+      }
+      la.items = w.locals[2]; la.num_items_ptr = &ctr->num_overflow;       // buckets those kernels handed back (heavy duplicates): LSD passes instead
       B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
     }
     if (!probe) break;

@@ -3,7 +3,7 @@
 
 usage: perf.py [logn=28] [reps=7] [cases=msb32,lsb32,lsb32v4,msb32v4,msb64,lsb64] [dist=uniform] [param=0]
 """
-import json, sys
+import json, os, sys
 import torch
 sys.path.insert(0, ".")
 import gpu_sort_b200 as gs
@@ -49,12 +49,16 @@ def main():
                 res_k = r.sorted_keys; res_v = r.sorted_values
             e1.record(); torch.cuda.synchronize()
             if it >= 2: times.append(e0.elapsed_time(e1))
+            if it == reps and os.environ.get("PERF_PROF"): gs.prof_enable(True)      # the last repetition is timed per kernel family
+        prof = None
+        if os.environ.get("PERF_PROF"):
+            prof = {k: [v[0], round(v[1], 4)] for k, v in gs.prof_report().items()}; gs.prof_enable(False)
         times.sort()
         s, x, bad, vbad = gs.check(res_k, res_v, key_type=kt)
         med = times[len(times) // 2]
         print(json.dumps({"case": case, "dist": dist, "param": param, "n": n, "ms_median": round(med, 4), "ms_best": round(times[0], 4),
                           "gkeys_s": round(n / med * 1e-6, 2), "temp_mb": round(tb / 2**20, 1), "sorted": bad == 0,
-                          "multiset_ok": (s, x) == ref_digest, "stable_iota": vbad == 0 if vb else None}), flush=True)
+                          "multiset_ok": (s, x) == ref_digest, "stable_iota": vbad == 0 if vb else None, "prof": prof}), flush=True)
         del src, vsrc, k0, k1, v0, v1, temp
         torch.cuda.empty_cache()
 
