@@ -48,6 +48,9 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatil
 __device__ __forceinline__ void sts_u64(uint32_t addr, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory"); }
 __device__ __forceinline__ uint32_t atoms_or(uint32_t addr, uint32_t v) { uint32_t o; asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory"); return o; }
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory"); return v; }
+template <typename T> __device__ __forceinline__ T lds_t(uint32_t addr) { if (sizeof(T) == 4) return (T)lds_u32(addr); else return (T)lds_u64(addr); }
 template <typename T> __device__ __forceinline__ void sts_t(uint32_t addr, T v) { if (sizeof(T) == 4) sts_u32(addr, (uint32_t)v); else sts_u64(addr, (uint64_t)v); }
 
 // A [off, off+cnt) element window of a global array as a 16-byte aligned byte range for bulk_g2s:

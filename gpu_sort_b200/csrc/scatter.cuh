@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < 8; ++j) woff += ((unsigned)j < w) ? sm.scratch[slot][j] : 0u;
     const uint32_t excl = woff + inc - c;
-    sm.cnt[slot][tid] = excl;
+    sm.cnt[slot][tid] = VB == 0 ? smem_u32(&sm.stage[slot][0]) + excl * (uint32_t)sizeof(K) : excl;      // keys-only: shared ADDRESS of the digit's first slot
     sm.goff[slot][tid] = (uint32_t)gstart - excl;          // n < 2^32: indices wrap correctly in 32 bits
     if (c > (uint32_t)TILE / 4) sm.skewed[slot] = 1;         // dominant digit: aggregate same-digit warps (see scatter_tile)
   };
@@ -603,90 +603,193 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
     V* __restrict__ vst = &sm.vstage[VB ? slot : 0][0];
     uint32_t* __restrict__ ctr = sm.cnt[slot];
 
-    // ---- keys: shared memory (TMA-staged) -> registers
-    mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
-    K key[IPT]; uint32_t pos[IPT];
-    {
-      const K* __restrict__ src = st + g.skew + tid;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < IPT; ++j) key[j] = src[j * THREADS];
-      } else {
-#pragma unroll
-        for (int j = 0; j < IPT; ++j) key[j] = (tid + j * THREADS < cnt) ? src[j * THREADS] : (K)~(K)0;
+    if constexpr (VB == 0) {
+      // ---- keys: shared memory (TMA-staged) -> registers.  All per-key shared-memory traffic below goes through explicit
+      // 32-bit shared addresses (async.cuh): the ranking counters hold the ADDRESS of every digit's next slot, so a key's
+      // atomicAdd returns where it goes and the reorder store needs no address arithmetic at all.
+      mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
+      K key[IPT]; uint32_t pos[IPT];
+      const uint32_t st_base = smem_u32(st), vst_base = smem_u32(vst), ctr_base = smem_u32(ctr), go_base = smem_u32(sm.goff[slot]);
+      {
+        const uint32_t src = st_base + (g.skew + tid) * (uint32_t)sizeof(K);
+        if (full) {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j) key[j] = lds_t<K>(src + j * THREADS * (uint32_t)sizeof(K));
+        } else {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j) key[j] = (tid + j * THREADS < cnt) ? lds_t<K>(src + j * THREADS * (uint32_t)sizeof(K)) : (K)~(K)0;
+        }
       }
-    }
-    if (a.tw_in) {
-      const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
-#pragma unroll
-      for (int j = 0; j < IPT; ++j) key[j] = tw_apply_in<K>(key[j], sg, fl, fp);
-    }
-    // ---- rank: the atomicAdd returns the key's final slot in the reorder buffer
-    if (!sm.skewed[slot]) {
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < IPT; ++j) pos[j] = atomicAdd(&ctr[digit_of<K>(key[j], shift, mask)], 1u);
-      } else {
-#pragma unroll
+      if (a.tw_in) {
+        const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+  #pragma unroll
+        for (int j = 0; j < IPT; ++j) key[j] = tw_apply_in<K>(key[j], sg, fl, fp);
+      }
+      V val[VB ? IPT : 1];
+      if (VB) {
+        const uint32_t vsrc = vst_base + (g.vskew + tid) * (uint32_t)sizeof(V);
+  #pragma unroll
         for (int j = 0; j < IPT; ++j)
-          if (tid + j * THREADS < cnt) pos[j] = atomicAdd(&ctr[digit_of<K>(key[j], shift, mask)], 1u);
+          if (full || tid + j * THREADS < cnt) val[j] = lds_t<V>(vsrc + j * THREADS * (uint32_t)sizeof(V));
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < IPT; ++j) {
-        const bool v = tid + j * THREADS < cnt;
-        const unsigned d = digit_of<K>(key[j], shift, mask);
-        const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
-        if (__all_sync(0xffffffffu, v && d == d0)) {
-          unsigned b = 0;
-          if (lane == 0) b = atomicAdd(&ctr[d0], 32u);
-          pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane;
-        } else if (v) {
-          pos[j] = atomicAdd(&ctr[d], 1u);
+      // ---- rank: the atomicAdd returns the shared address of the key's final slot in the reorder buffer
+      if (!sm.skewed[slot]) {
+        if (full) {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j) pos[j] = atoms_add(ctr_base + digit_of<K>(key[j], shift, mask) * 4u, (uint32_t)sizeof(K));
+        } else {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j)
+            if (tid + j * THREADS < cnt) pos[j] = atoms_add(ctr_base + digit_of<K>(key[j], shift, mask) * 4u, (uint32_t)sizeof(K));
+        }
+      } else {
+  #pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+          const bool v = tid + j * THREADS < cnt;
+          const unsigned d = digit_of<K>(key[j], shift, mask);
+          const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
+          if (__all_sync(0xffffffffu, v && d == d0)) {
+            unsigned b = 0;
+            if (lane == 0) b = atoms_add(ctr_base + d0 * 4u, 32u * (uint32_t)sizeof(K));
+            pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane * (uint32_t)sizeof(K);
+          } else if (v) {
+            pos[j] = atoms_add(ctr_base + d * 4u, (uint32_t)sizeof(K));
+          }
         }
       }
-    }
-    V val[VB ? IPT : 1];
-    if (VB) {
-      const V* __restrict__ vsrc = vst + g.vskew + tid;
-#pragma unroll
-      for (int j = 0; j < IPT; ++j)
-        if (full || tid + j * THREADS < cnt) val[j] = vsrc[j * THREADS];
-    }
-    __syncthreads();          // every thread has its keys (and values) in registers: the staging buffers become the reorder buffers
-#pragma unroll
-    for (int j = 0; j < IPT; ++j)
-      if (full || tid + j * THREADS < cnt) { st[pos[j]] = key[j]; if (VB) vst[pos[j]] = val[j]; }
-    __syncthreads();          // reorder complete; geom[slot ^ 1] (written by the producer above) is visible
-    // ---- digit owners prepare the next tile while everybody writes this one out
-    if (tid < RADIX) prepare(slot ^ 1);
-    // ---- coalesced write-out: consecutive positions of one digit are consecutive output addresses
-    const uint32_t* __restrict__ go = sm.goff[slot];
-    K* __restrict__ kout = reinterpret_cast<K*>(a.keys_out);
-    V* __restrict__ vout = reinterpret_cast<V*>(a.vals_out);
-    if (a.tw_out) {
-      const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
-#pragma unroll
-      for (int j = 0; j < IPT; ++j) {
-        const uint32_t p = j * THREADS + tid;
-        if (full || p < cnt) {
-          const K k = st[p];
-          const uint32_t d = digit_of<K>(k, shift, mask);
-          const uint32_t o = go[d] + p;
-          st_global<K>(kout, o, tw_apply_out<K>(k, sg, fl, fp));
-          if (VB) st_global<V>(vout, o, vst[p]);
+      __syncthreads();          // every thread has its keys (and values) in registers: the staging buffers become the reorder buffers
+      {
+        // value slot of a key: same element index as its key slot
+        auto vaddr = [&](uint32_t kaddr) { return sizeof(V) == sizeof(K) ? kaddr + (vst_base - st_base) : vst_base + ((kaddr - st_base) / (uint32_t)sizeof(K)) * (uint32_t)sizeof(V); };
+        if (full) {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j) { sts_t<K>(pos[j], key[j]); if (VB) sts_t<V>(vaddr(pos[j]), val[j]); }
+        } else {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j)
+            if (tid + j * THREADS < cnt) { sts_t<K>(pos[j], key[j]); if (VB) sts_t<V>(vaddr(pos[j]), val[j]); }
         }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < IPT; ++j) {
-        const uint32_t p = j * THREADS + tid;
-        if (full || p < cnt) {
-          const K k = st[p];
-          const uint32_t d = digit_of<K>(k, shift, mask);
-          const uint32_t o = go[d] + p;
+      __syncthreads();          // reorder complete; geom[slot ^ 1] (written by the producer above) is visible
+      // ---- digit owners prepare the next tile while everybody writes this one out
+      if (tid < RADIX) prepare(slot ^ 1);
+      // ---- coalesced write-out: consecutive positions of one digit are consecutive output addresses
+      K* __restrict__ kout = reinterpret_cast<K*>(a.keys_out);
+      V* __restrict__ vout = reinterpret_cast<V*>(a.vals_out);
+      {
+        const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+        const bool two = a.tw_out != 0;
+        const uint32_t ksrc = st_base + tid * (uint32_t)sizeof(K), vsrc = vst_base + tid * (uint32_t)sizeof(V);
+        auto emit = [&](int j) {
+          const uint32_t p = j * THREADS + tid;
+          K k = lds_t<K>(ksrc + j * THREADS * (uint32_t)sizeof(K));
+          const uint32_t o = lds_u32(go_base + digit_of<K>(k, shift, mask) * 4u) + p;
+          if (two) k = tw_apply_out<K>(k, sg, fl, fp);
           st_global<K>(kout, o, k);
-          if (VB) st_global<V>(vout, o, vst[p]);
+        };
+        if (full) {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j) emit(j);
+        } else {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j) {
+            const uint32_t p = j * THREADS + tid;
+            if (p < cnt) {
+              K k = lds_t<K>(ksrc + j * THREADS * (uint32_t)sizeof(K));
+              const uint32_t o = lds_u32(go_base + digit_of<K>(k, shift, mask) * 4u) + p;
+              if (two) k = tw_apply_out<K>(k, sg, fl, fp);
+              st_global<K>(kout, o, k);
+              if (VB) st_global<V>(vout, o, lds_t<V>(vsrc + j * THREADS * (uint32_t)sizeof(V)));
+            }
+          }
+        }
+      }
+    } else {
+      // ---- keys: shared memory (TMA-staged) -> registers
+      mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
+      K key[IPT]; uint32_t pos[IPT];
+      {
+        const K* __restrict__ src = st + g.skew + tid;
+        if (full) {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j) key[j] = src[j * THREADS];
+        } else {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j) key[j] = (tid + j * THREADS < cnt) ? src[j * THREADS] : (K)~(K)0;
+        }
+      }
+      if (a.tw_in) {
+        const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+  #pragma unroll
+        for (int j = 0; j < IPT; ++j) key[j] = tw_apply_in<K>(key[j], sg, fl, fp);
+      }
+      // ---- rank: the atomicAdd returns the key's final slot in the reorder buffer
+      if (!sm.skewed[slot]) {
+        if (full) {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j) pos[j] = atomicAdd(&ctr[digit_of<K>(key[j], shift, mask)], 1u);
+        } else {
+  #pragma unroll
+          for (int j = 0; j < IPT; ++j)
+            if (tid + j * THREADS < cnt) pos[j] = atomicAdd(&ctr[digit_of<K>(key[j], shift, mask)], 1u);
+        }
+      } else {
+  #pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+          const bool v = tid + j * THREADS < cnt;
+          const unsigned d = digit_of<K>(key[j], shift, mask);
+          const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
+          if (__all_sync(0xffffffffu, v && d == d0)) {
+            unsigned b = 0;
+            if (lane == 0) b = atomicAdd(&ctr[d0], 32u);
+            pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane;
+          } else if (v) {
+            pos[j] = atomicAdd(&ctr[d], 1u);
+          }
+        }
+      }
+      V val[VB ? IPT : 1];
+      if (VB) {
+        const V* __restrict__ vsrc = vst + g.vskew + tid;
+  #pragma unroll
+        for (int j = 0; j < IPT; ++j)
+          if (full || tid + j * THREADS < cnt) val[j] = vsrc[j * THREADS];
+      }
+      __syncthreads();          // every thread has its keys (and values) in registers: the staging buffers become the reorder buffers
+  #pragma unroll
+      for (int j = 0; j < IPT; ++j)
+        if (full || tid + j * THREADS < cnt) { st[pos[j]] = key[j]; if (VB) vst[pos[j]] = val[j]; }
+      __syncthreads();          // reorder complete; geom[slot ^ 1] (written by the producer above) is visible
+      // ---- digit owners prepare the next tile while everybody writes this one out
+      if (tid < RADIX) prepare(slot ^ 1);
+      // ---- coalesced write-out: consecutive positions of one digit are consecutive output addresses
+      const uint32_t* __restrict__ go = sm.goff[slot];
+      K* __restrict__ kout = reinterpret_cast<K*>(a.keys_out);
+      V* __restrict__ vout = reinterpret_cast<V*>(a.vals_out);
+      if (a.tw_out) {
+        const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+  #pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+          const uint32_t p = j * THREADS + tid;
+          if (full || p < cnt) {
+            const K k = st[p];
+            const uint32_t d = digit_of<K>(k, shift, mask);
+            const uint32_t o = go[d] + p;
+            st_global<K>(kout, o, tw_apply_out<K>(k, sg, fl, fp));
+            if (VB) st_global<V>(vout, o, vst[p]);
+          }
+        }
+      } else {
+  #pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+          const uint32_t p = j * THREADS + tid;
+          if (full || p < cnt) {
+            const K k = st[p];
+            const uint32_t d = digit_of<K>(k, shift, mask);
+            const uint32_t o = go[d] + p;
+            st_global<K>(kout, o, k);
+            if (VB) st_global<V>(vout, o, vst[p]);
+          }
         }
       }
     }

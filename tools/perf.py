@@ -34,7 +34,8 @@ def main():
         temp = torch.empty(tb, dtype=torch.uint8, device="cuda")
         times = []
         res_k = res_v = None
-        for it in range(reps + 2):
+        PROF_REPS = 4 if os.environ.get("PERF_PROF") else 0
+        for it in range(reps + 2 + PROF_REPS):
             k0.copy_(src)
             if vb: v0.copy_(vsrc)
             torch.cuda.synchronize()
@@ -48,11 +49,11 @@ def main():
                 r = gs.rdxsrt_unstable_sort(k0, v0, n, k1, v1, workspace=temp, key_type=kt)
                 res_k = r.sorted_keys; res_v = r.sorted_values
             e1.record(); torch.cuda.synchronize()
-            if it >= 2: times.append(e0.elapsed_time(e1))
-            if it == reps and os.environ.get("PERF_PROF"): gs.prof_enable(True)      # the last repetition is timed per kernel family
+            if it >= 2 and it < reps + 2: times.append(e0.elapsed_time(e1))
+            if it == reps + 1 and os.environ.get("PERF_PROF"): gs.prof_enable(True)      # PROF_REPS more repetitions, timed per kernel family
         prof = None
         if os.environ.get("PERF_PROF"):
-            prof = {k: [v[0], round(v[1], 4)] for k, v in gs.prof_report().items()}; gs.prof_enable(False)
+            prof = {k: [v[0] // PROF_REPS, round(v[1] / PROF_REPS, 4)] for k, v in gs.prof_report().items()}; gs.prof_enable(False)
         times.sort()
         s, x, bad, vbad = gs.check(res_k, res_v, key_type=kt)
         med = times[len(times) // 2]
