@@ -36,6 +36,8 @@ WORKLOADS = {
     "cfg2": (28, 32, 0, "msb", "uniform", 0, 3, "2^28 uniform uint32 keys, keys-only, MSB hybrid radix sort"),
     "cfg3": (28, 32, 4, "lsb", "uniform", 0, 3, "2^28 uint32 key + uint32 value pairs, stable sort (cub::DeviceRadixSort call shape)"),
     "cfg4": (29, 64, 0, "msb", "zipf_hash", 0, 3, "2^29 uint64 keys, Zipf-skewed, MSB hybrid"),
+    # one GPU's share of BASELINE config 5 (2^32 pairs over 8 GPUs): the single-GPU / reference-arm form of the multi-GPU workload
+    "cfg5": (29, 32, 4, "lsb", "uniform", 0, 4, "2^29 uint32 key + uint32 value pairs (one GPU's share of config 5), stable sort"),
 }
 
 
@@ -181,8 +183,9 @@ def run_ours_single(args, wl):
     for _ in range(args.steps):
         restore(); step()
     torch.cuda.synchronize()
+    launches_total = gs.prof_launches()          # every launch site of the library counts itself while profiling is on
     prof = gs.prof_report(); gs.prof_enable(False)
-    launches_per_step = sum(c for c, _ in prof.values()) / args.steps
+    launches_per_step = launches_total / args.steps
     dom = max(prof.items(), key=lambda kv: kv[1][1])
     dom_name, (dom_cnt, dom_ms) = dom
     kbytes, vbytes = kbits // 8, vb
@@ -191,7 +194,8 @@ def run_ours_single(args, wl):
     # write every key (+ value) once; each is preceded by one histogram read of the keys; the on-chip sort reads and writes
     # every key (+ value) once.  Both entry points run the same MSD engine (stable or not).
     fam_bytes = {"scatter": (S - 1) * sweep_bytes, "scatter_stable": (S - 1) * sweep_bytes, "scatter_onesweep": S * sweep_bytes,
-                 "tile_hist": (S - 1) * n * kbytes, "hist_all": n * kbytes, "local_sort_lsd": sweep_bytes, "local_sort_count": sweep_bytes}
+                 "tile_hist": (S - 1) * n * kbytes, "hist_all": n * kbytes, "local_sort_lsd": sweep_bytes, "local_sort_count": sweep_bytes,
+                 "local_sort_rank": sweep_bytes, "local_sort_bitmap": sweep_bytes}
     dom_bytes = fam_bytes.get(dom_name, sweep_bytes)
     dom_ms_per_step = dom_ms / args.steps
     peak, peak_src = peaks()
@@ -233,7 +237,8 @@ def run_ours_single(args, wl):
                "ms_per_step": round(dt * 1e3, 3), "steps": e2e_steps, "entry": "b200_msb_sort_host (pinned host buffers)"}
 
     line = {"metric": "Gkeys/s", "value": round(n / (mean * 1e-3) / 1e9, 3), "unit": "Gkeys/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(mean, 4), "ms_median": round(med, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(mean, 4), "ms_median": round(med, 4), "value_median": round(n / (med * 1e-3) / 1e9, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32" if kbits == 32 else "u64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "n": n, "path": path, "key_bits": kbits, "value_bytes": vb, "dist": dist,
                        "l2": "inputs (>= 1 GiB) larger than the 126 MB L2; input restored by an untimed D2D copy between steps",
@@ -248,50 +253,93 @@ def run_ours_single(args, wl):
 
 
 def run_ours_multi(args, rank, world):
-    """Weak scaling: N x 2^logn keys of one global array (keys-only u32, uniform); gpu_sort_b200/dist.py."""
+    """BASELINE config 5, weak-scaled: every rank holds 2^logn (default 2^29) uint32 key + uint32 value pairs of ONE global array
+    (N = 8 -> 2^32 pairs), sorted with the multi-GPU path of gpu_sort_b200/dist.py (ExchangeSorter: per-tile digit counts,
+    256-bin count all-gather, stable scatter straight into the peers' receive buffers over NVLink, segmented finish)."""
     import torch.distributed as dist
     import gpu_sort_b200 as gs
     from gpu_sort_b200 import dist as gd
-    logn = args.logn or 28
+    pairs = args.workload != "cfg2"
+    logn = args.logn or (29 if pairs else 28)
     n_l = 1 << logn
     total = n_l * world
-    pairs = args.workload == "cfg5"
     src = torch.empty(n_l, dtype=torch.int32, device="cuda")
     gs.generate_keys(src, seed=0, dist="uniform", start=rank * n_l, total=total)
     vsrc = gs.iota(torch.empty(n_l, dtype=torch.int32, device="cuda"), start=rank * n_l) if pairs else None
     keys = torch.empty_like(src); vals = torch.empty_like(vsrc) if pairs else None
     din = gs.check(src, vsrc, key_type=gs.KEY_U32)[0]
-    res = {}
 
     def restore():
         keys.copy_(src)
         if pairs:
             vals.copy_(vsrc)
 
-    sorter = gd.DistSorter(n_l, torch.int32, torch.int32 if pairs else None, key_type=gs.KEY_U32, fused=not args.nccl_exchange)
+    if args.nccl_exchange:
+        sorter = gd.DistSorter(n_l, torch.int32, torch.int32 if pairs else None, key_type=gs.KEY_U32, fused=False)
+        res = {}
 
-    def step():
-        res["k"], res["v"], res["info"] = sorter.sort(keys, vals)
+        def step():
+            res["out"] = sorter.sort(keys, vals)
+        fetch = lambda: res["out"]
+    else:
+        sorter = gd.ExchangeSorter(n_l, torch.int32, torch.int32 if pairs else None, key_type=gs.KEY_U32)
+
+        def step():
+            sorter.sort(keys, vals)          # enqueue only: no host read-back inside the timed region
+        fetch = sorter.result
 
     clocks = ClockSampler(torch.cuda.current_device()); clocks.start()
     ms, wall = time_steps(step, restore, args.steps, args.warmup, dist.barrier)
     clk = clocks.stop()
-    restore(); pinfo = sorter.sort(keys, vals, profile=True)[2]; phases = dict(pinfo.get("phases_ms", {}), kernels=pinfo.get("kernels_ms"))
+    rk, rv, info = fetch()
     t = torch.tensor([float(np.sum(ms))], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)                       # max over ranks of the device-timed K steps
     total_ms = float(t.item())
-    # validation: per-rank sortedness, boundary order between neighbouring ranks, global multiset digest
-    s, x, bad, vbad = gs.check(res["k"], res["v"], key_type=gs.KEY_U32)
-    mine = res["k"].view(torch.int32)
+    tm = torch.tensor([float(np.median(ms))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    # validation: per-rank sortedness (+ stability), boundary order between neighbouring ranks, global multiset digest
+    s, x, bad, vbad = gs.check(rk, rv, key_type=gs.KEY_U32) if rk.numel() else (0, 0, 0, 0)
+    mine = rk.view(torch.int32)
     lo = int(mine[0].item()) & 0xFFFFFFFF if mine.numel() else None
     hi = int(mine[-1].item()) & 0xFFFFFFFF if mine.numel() else None
-    rec = {"sum": s, "bad": bad, "vbad": vbad if pairs else 0, "n": mine.numel(), "lo": lo, "hi": hi, "din": din}
+    rec = {"sum": s, "bad": bad, "vbad": vbad if pairs else 0, "n": mine.numel(), "lo": lo, "hi": hi, "din": din, "path": info.get("path", "key-range")}
     recs = [None] * world
     dist.all_gather_object(recs, rec)
     ok = all(r["bad"] == 0 and r["vbad"] == 0 for r in recs) and sum(r["n"] for r in recs) == total
     nz = [r for r in recs if r["n"]]
     ok = ok and all(nz[i]["hi"] <= nz[i + 1]["lo"] for i in range(len(nz) - 1))
     ok = ok and sum(r["sum"] for r in recs) % (1 << 64) == sum(r["din"] for r in recs) % (1 << 64)
+    # ---- kernels launched per step and phase times: one more sort with every launch bracketed by CUDA events
+    restore()
+    phases, launches = {}, None
+    if not args.nccl_exchange:
+        sorter.sort(keys, vals, profile=True)
+        phases = dict(sorter.profile["phases_ms"], kernels=sorter.profile["kernels_ms"])
+        launches = sorter.profile.get("launches")
+    # ---- the same per-GPU workload on ONE GPU (rank 0's shard, the single-GPU stable sort): the weak-scaling reference point
+    local = None
+    if rank == 0 and not args.no_local_ref:
+        k0, k1 = torch.empty_like(src), torch.empty_like(src)
+        v0 = torch.empty_like(vsrc) if pairs else None; v1 = torch.empty_like(vsrc) if pairs else None
+        dk0 = gs.DoubleBuffer(k0, k1); dv0 = gs.DoubleBuffer(v0, v1) if pairs else None
+        tb = gs.DeviceRadixSort._run(None, dk0, dv0, n_l, 0, None, False, None, gs.KEY_U32)
+        temp = torch.empty(tb, dtype=torch.uint8, device="cuda")
+        lt = []
+        for it in range(5):
+            k0.copy_(src)
+            if pairs:
+                v0.copy_(vsrc)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gs.DeviceRadixSort._run(temp, gs.DoubleBuffer(k0, k1), gs.DoubleBuffer(v0, v1) if pairs else None, n_l, 0, None, False, None, gs.KEY_U32)
+            e1.record(); torch.cuda.synchronize()
+            if it >= 2:
+                lt.append(e0.elapsed_time(e1))
+        lm = float(np.median(lt))
+        local = {"ms": round(lm, 4), "value": round(n_l / (lm * 1e-3) / 1e9, 3), "unit": "Gkeys/s",
+                 "what": f"single-GPU stable sort (b200_lsb_sort) of one rank's 2^{logn} items, same process, other ranks idle"}
+        del k0, k1, v0, v1, temp
+    dist.barrier()
     # ---- end to end: every rank's shard starts in pinned host memory and the sorted range it ends up owning returns there
     e2e = None
     if not args.no_e2e:
@@ -306,10 +354,11 @@ def run_ours_multi(args, rank, world):
             keys.copy_(hk, non_blocking=True)
             if pairs:
                 vals.copy_(hv, non_blocking=True)
-            k, v, info = sorter.sort(keys, vals)
-            ho[:info["count"]].copy_(k, non_blocking=True)
+            step()
+            k, v, inf = fetch()
+            ho[:inf["count"]].copy_(k, non_blocking=True)
             if pairs:
-                hvo[:info["count"]].copy_(v, non_blocking=True)
+                hvo[:inf["count"]].copy_(v, non_blocking=True)
             torch.cuda.synchronize()
         e2e_step()
         dist.barrier()
@@ -322,20 +371,30 @@ def run_ours_multi(args, rank, world):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         bpk = 8 if pairs else 4
         e2e = {"value": round(total / float(dt.item()) / 1e9, 3), "unit": "Gkeys/s", "h2d_bytes_per_step": total * bpk, "d2h_bytes_per_step": total * bpk,
-               "ms_per_step": round(float(dt.item()) * 1e3, 3), "entry": "DistSorter.sort with pinned host shards (H2D + sort + D2H per rank)"}
+               "ms_per_step": round(float(dt.item()) * 1e3, 3), "entry": "ExchangeSorter.sort + result with pinned host shards (H2D + sort + D2H per rank)"}
     if rank != 0:
         return None
     mean = total_ms / args.steps
+    med = float(tm.item())
     kb = 8 if pairs else 4
-    return {"metric": "Gkeys/s", "value": round(total / (mean * 1e-3) / 1e9, 3), "unit": "Gkeys/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(mean, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"{'cfg5-style pairs' if pairs else 'cfg2 weak-scaled'}: 2^{logn} uniform uint32 {'key+value pairs' if pairs else 'keys'} per GPU, one global array of {world}x2^{logn}, "
-                                   "histogram all-reduce + key-range all-to-all over NVLink + local sort", "n_total": total, "n_per_gpu": n_l, "value_bytes": 4 if pairs else 0,
+    value = total / (mean * 1e-3) / 1e9
+    nv_bytes = int(n_l * kb * (world - 1) / world)
+    xms = phases.get("scatter")
+    line = {"metric": "Gkeys/s", "value": round(value, 3), "unit": "Gkeys/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(mean, 4), "ms_median": round(med, 4), "value_median": round(total / (med * 1e-3) / 1e9, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": (f"cfg5: uint32 key + uint32 value pairs, 2^{logn} per GPU of one global array of {world}x2^{logn}" + (" (= 2^32 pairs, BASELINE config 5)" if total == 1 << 32 else "")
+                                    if pairs else f"cfg2 weak-scaled: 2^{logn} uniform uint32 keys per GPU of one global array of {world}x2^{logn}")
+                                   + "; per-tile digit counts + 256-bin count all-gather + stable scatter into the peers' receive buffers over NVLink + segmented finish",
+                       "n_total": total, "n_per_gpu": n_l, "value_bytes": 4 if pairs else 0, "path": "nccl all_to_all baseline" if args.nccl_exchange else sorted(set(r["path"] for r in recs)),
                        "l2": "inputs larger than L2; restored by an untimed D2D copy between steps", "timing": "CUDA events per step on each rank; max over ranks of the K-step sum"},
-            "exchange": {"imbalance": round(res["info"]["imbalance"], 4), "nvlink_bytes_out_per_gpu": int(n_l * kb * (world - 1) / world),
-                         "fused_peer_scatter": bool(res["info"]["fused"]), "phases_ms_rank0": phases},
-            "clocks": clk, "gpu_launches": int(args.steps * 45), "gpu_launches_note": "about 45 library kernels per rank per step (histogram, range partition, 4 levels x 7, on-chip sorts)",
+            "exchange": {"imbalance": round(float(info.get("imbalance", 1.0)), 4), "nvlink_bytes_out_per_gpu": nv_bytes,
+                         "nvlink_gbs_per_gpu_during_scatter": round(nv_bytes / (xms * 1e-3) / 1e9, 1) if xms else None, "phases_ms_rank0": phases},
+            "single_gpu_same_workload": local,
+            "weak_scaling_efficiency_vs_single_gpu_same_workload": round(value / (world * local["value"]), 3) if local else None,
+            "clocks": clk, "gpu_launches": int(launches * args.steps) if launches else None, "gpu_launches_per_step": launches,
             "e2e": e2e, "verified": bool(ok), "wall_s_timed_region": round(wall, 3)}
+    return line
 
 
 def run_reference(args, wl):
@@ -350,12 +409,14 @@ def run_reference(args, wl):
         return {"impl": "reference", "metric": "Gkeys/s", "value": cb["value"], "unit": "Gkeys/s", "n_gpus": 1, "steps": 1, "warmup": 0, "higher_is_better": True,
                 "config": {"workload": f"{args.workload}: {desc} (bounded CPU sample)"}, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    import gpu_sort_b200 as gs           # only for the shared input generator + result check (b200_util_*)
-    kt = gs.KEY_U32 if kbits == 32 else gs.KEY_U64
+    # inputs and result check come from the CPU oracle and torch: this arm must not load libb200sort.so
+    from tests import oracle_lib
+    orc = oracle_lib.load()
     kdt = torch.int32 if kbits == 32 else torch.int64
     vdt = torch.int32 if vb == 4 else torch.int64
-    src = torch.empty(n, dtype=kdt, device="cuda"); gs.generate_keys(src, seed=0, dist=dist, param=param)
-    vsrc = gs.iota(torch.empty(n, dtype=vdt, device="cuda")) if vb else None
+    keys_np = orc.gen_keys(n, kbits, seed=0, dist=dist, param=param)          # same generator and seed as the product arm (b200_util_generate_keys)
+    src = torch.from_numpy(keys_np.view(np.int32 if kbits == 32 else np.int64)).cuda()
+    vsrc = torch.arange(n, dtype=vdt, device="cuda") if vb else None
     k0, k1 = torch.empty_like(src), torch.empty_like(src)
     v0 = torch.empty_like(vsrc) if vb else None; v1 = torch.empty_like(vsrc) if vb else None
     P = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
@@ -414,10 +475,16 @@ def run_reference(args, wl):
             step()              # leave the result of the measured entry in place for the check below
     finally:
         os.dup2(saved, 1); os.close(devnull)
-    s, x, bad, _ = gs.check(res["k"], res["v"], key_type=kt)
-    mean = float(np.mean(ms))
+    out_k = res["k"].cpu().numpy().view(np.uint32 if kbits == 32 else np.uint64)
+    bad = int(orc.count_unsorted(out_k, "u32" if kbits == 32 else "u64"))
+    out_v = res["v"].cpu().numpy().view(np.uint32 if vb == 4 else np.uint64) if vb else None
+    in_v = np.arange(n, dtype=np.uint32 if vb == 4 else np.uint64) if vb else None
+    same_multiset = orc.digest(out_k, out_v) == orc.digest(keys_np, in_v)
+    bad = bad if same_multiset else max(bad, 1)
+    mean = float(np.mean(ms)); med = float(np.median(ms))
     line = {"impl": "reference", "metric": "Gkeys/s", "value": round(n / (mean * 1e-3) / 1e9, 3), "unit": "Gkeys/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(mean, 4), "ms_median": round(float(np.median(ms)), 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(mean, 4), "ms_median": round(med, 4), "value_median": round(n / (med * 1e-3) / 1e9, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32" if kbits == 32 else "u64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "n": n, "path": path, "api": api}, "clocks": clk, "verified": bad == 0}
     if shipped is not None:
@@ -453,22 +520,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS) + ["cfg5"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS), help="default: cfg2 on one GPU, cfg5 on several")
     ap.add_argument("--logn", type=int, default=0, help="override log2(keys per GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-local-ref", action="store_true", help="multi-GPU: skip the single-GPU reference point of the same per-GPU workload")
     ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: NCCL all_to_all_single instead of the fused peer-memory scatter")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        args.workload = "cfg2" if world == 1 else "cfg5"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         if torch.cuda.is_available():
             torch.cuda.set_device(0)
-        wl = WORKLOADS["cfg3" if args.workload == "cfg5" else args.workload]
-        print(json.dumps(run_reference(args, wl)), flush=True)
+        print(json.dumps(run_reference(args, WORKLOADS[args.workload])), flush=True)
         return 0
 
     if not torch.cuda.is_available():
@@ -482,7 +551,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     else:
-        line = run_ours_single(args, WORKLOADS["cfg3" if args.workload == "cfg5" else args.workload])
+        line = run_ours_single(args, WORKLOADS[args.workload])
     if rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
     return 0

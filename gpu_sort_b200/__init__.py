@@ -63,6 +63,11 @@ def _load():
     lib.b200_msb_sort_bits.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, i32, vp, P(sz), vp, P(vp), P(vp)]
     lib.b200_range_partition_to.restype = i32
     lib.b200_range_partition_to.argtypes = [vp, P(sz), vp, vp, u64, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]
+    if hasattr(lib, "b200_exchange_hist") or not os.environ.get("B200SORT_LIB"):
+        lib.b200_exchange_hist.restype = i32
+        lib.b200_exchange_hist.argtypes = [vp, P(sz), vp, u64, i32, i32, i32, vp, vp]
+        lib.b200_exchange_scatter.restype = i32
+        lib.b200_exchange_scatter.argtypes = [vp, P(sz), vp, vp, u64, i32, i32, i32, vp, i32, i32, u64, vp, vp, vp, vp, vp, vp]
     lib.b200_msb_sort_host.restype = i32
     lib.b200_msb_sort_host.argtypes = [vp, vp, u64, vp, vp, i32, i32]
     lib.b200_lsb_sort_host.restype = i32
@@ -77,6 +82,8 @@ def _load():
     lib.b200_util_iota.argtypes = [vp, u64, u64, i32, vp]
     lib.b200_prof_enable.restype = i32
     lib.b200_prof_enable.argtypes = [i32]
+    if hasattr(lib, "b200_prof_launches"):
+        lib.b200_prof_launches.restype = ctypes.c_ulonglong
     lib.b200_prof_report.restype = i32
     lib.b200_prof_report.argtypes = [ctypes.c_char_p, sz]
     lib.b200_util_check.restype = i32
@@ -363,6 +370,11 @@ def check(keys: torch.Tensor, values: Optional[torch.Tensor] = None, descending=
 def prof_enable(on: bool = True):
     """Bracket every kernel launch of the library with CUDA events (b200_prof_enable)."""
     _check(lib.b200_prof_enable(int(on)), "b200_prof_enable")
+
+
+def prof_launches() -> int:
+    """Kernels launched by the library since prof_enable(True) (b200_prof_launches)."""
+    return int(lib.b200_prof_launches())
 
 
 def prof_report() -> dict:

@@ -17,6 +17,7 @@ using namespace b200;
 // ---- per-kernel timing (sort_api.h: ProfScope) -----------------------------------------------------------------
 namespace b200 {
 int g_prof_enabled = 0;
+unsigned long long g_prof_launches = 0;
 namespace {
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 std::mutex g_prof_mu;
@@ -134,8 +135,11 @@ int b200_prof_enable(int enable) {
   for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
   g_prof_recs.clear();
   g_prof_enabled = enable ? 1 : 0;
+  g_prof_launches = 0;
   return 0;
 }
+
+unsigned long long b200_prof_launches(void) { return g_prof_launches; }
 
 int b200_prof_report(char* buf, size_t cap) {
   std::lock_guard<std::mutex> lock(g_prof_mu);
@@ -237,6 +241,28 @@ int b200_range_partition_to(void* d_temp, size_t* temp_bytes, const void* d_keys
   DISPATCH_KV(kb, value_bytes, (range_partition_impl<K, V>(d_temp, temp_bytes, d_keys_in, d_values_in, nullptr, nullptr, num_items, tw, bits,
                                                            d_splitters, num_parts, d_local_counts, d_part_offsets, d_dst_keys, d_dst_values,
                                                            d_dst_base, s)));
+}
+
+int b200_exchange_hist(void* d_temp, size_t* temp_bytes, const void* d_keys_in, uint64_t num_items, int key_type, int value_bytes, int bucket_bits,
+                       uint64_t* d_hist, b200_stream_t stream) {
+  Twiddle tw; int kb;
+  if (!make_twiddle(key_type, 0, &tw, &kb) || temp_bytes == nullptr) return (int)cudaErrorInvalidValue;
+  if (d_temp != nullptr && d_hist == nullptr) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_KV(kb, value_bytes, (exchange_hist_impl<K, V>(d_temp, temp_bytes, d_keys_in, num_items, tw, bucket_bits, d_hist, s)));
+}
+
+int b200_exchange_scatter(void* d_temp, size_t* temp_bytes, const void* d_keys_in, const void* d_values_in, uint64_t num_items, int key_type,
+                          int value_bytes, int bucket_bits, const uint64_t* d_count_matrix, int num_ranks, int rank, uint64_t capacity,
+                          const uint64_t* d_dst_keys, const uint64_t* d_dst_values, uint64_t* d_seg_begin, uint64_t* d_seg_end, uint64_t* d_info,
+                          b200_stream_t stream) {
+  Twiddle tw; int kb;
+  if (!make_twiddle(key_type, 0, &tw, &kb) || temp_bytes == nullptr) return (int)cudaErrorInvalidValue;
+  if (d_temp != nullptr && (d_count_matrix == nullptr || d_dst_keys == nullptr || (value_bytes && d_dst_values == nullptr) || d_seg_begin == nullptr ||
+                            d_seg_end == nullptr || d_info == nullptr)) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_KV(kb, value_bytes, (exchange_scatter_impl<K, V>(d_temp, temp_bytes, d_keys_in, d_values_in, num_items, tw, bucket_bits, d_count_matrix, num_ranks,
+                                                            rank, capacity, d_dst_keys, d_dst_values, d_seg_begin, d_seg_end, d_info, s)));
 }
 
 int b200_range_partition(void* d_temp, size_t* temp_bytes, const void* d_keys_in, const void* d_values_in, void* d_keys_out,

@@ -23,7 +23,7 @@ namespace b200 {
 
 constexpr int RANK_BITS = 16;
 constexpr int RANK_ENT = (1 << RANK_BITS) / 16;       // 16 cells per entry
-constexpr int RANK_EXTRA = 8;          // (<= 15: the scan counts the listed copies of an entry in a 4-bit field)
+constexpr int RANK_EXTRA = 15;         // (<= 15: the scan counts the listed copies of an entry in a 4-bit field)
 
 template <typename K, int VB, int THREADS, int IPT, bool STABLE>
 struct RankSmem {

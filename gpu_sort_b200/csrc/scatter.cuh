@@ -55,6 +55,11 @@ struct ScatterArgs {
   const uint32_t* splitters; int num_parts;     // MODE_RANGE: digit = #{ j < num_parts-1 : splitters[j] <= (key >> shift) }
   const uint64_t* dst_keys; const uint64_t* dst_vals;   // MODE_RANGE: [num_parts] base ADDRESS of every destination's key / value buffer
                                                         // (nullptr: keys_out / vals_out for all); bins[d] = first index inside that buffer
+  const uint8_t* digit_dest;      // scatter_stable_fast_kernel<PEER> (multi-GPU exchange): [256] which of the dst_keys / dst_vals buffers
+                                  // (the peer GPUs' receive buffers) an exchange BUCKET goes to; bucket = digit >> xshift (several digits
+                                  // share a bucket so that a tile's run for a bucket is long enough for NVLink: >= 128-byte pieces reach
+                                  // 700 GB/s, 64-byte pieces 420, profiles/r02_ubench_peer.jsonl); bins[b] = the bucket's first index there
+  int xshift;
 };
 
 constexpr int MAX_PARTS = 16;
@@ -804,7 +809,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
 // and no padding correction), destinations are already in shared memory when the tile starts, values are read before the
 // first barrier so keys and values are reordered in one phase: four block barriers per tile instead of seven.
 // ===============================================================================================================
-template <typename K, int VB, int THREADS, int IPT>
+template <typename K, int VB, int THREADS, int IPT, bool PEER = false>
 struct StableFastSmem {
   static constexpr int TILE = THREADS * IPT;
   static constexpr int WARPS = THREADS / 32;
@@ -812,6 +817,10 @@ struct StableFastSmem {
   static constexpr int SLACK = 16 / sizeof(K), VSLACK = 16 / sizeof(V);
   alignas(16) K stage[2][TILE + SLACK];
   alignas(16) V vstage[VB ? 2 : 1][VB ? TILE + VSLACK : 1];
+  uint64_t dstk[PEER ? MAX_PARTS : 1], dstv[PEER ? MAX_PARTS : 1];   // PEER: base addresses of the destination buffers
+  uint8_t gdst[PEER ? 2 : 1][PEER ? RADIX : 4];                      // PEER: per digit, which destination buffer
+  uint32_t bsum[PEER ? RADIX : 1];                                   // PEER (inside prepare only): per bucket, keys of it in this source's earlier tiles
+  uint16_t bexcl[PEER ? RADIX : 2];                                  // PEER (inside prepare only): per bucket, where its keys start inside the tile
   uint32_t goff[2][RADIX];          // per digit: (global start - start inside the tile) mod 2^32; output index = goff[d] + position
   alignas(16) uint32_t match[2][WARPS * RADIX];   // per-warp match masks, two alternating sets (always zero between rows)
   alignas(16) uint16_t wcnt[WARPS * RADIX];       // per-warp counters, later per-warp start positions; zero at tile start
@@ -821,10 +830,10 @@ struct StableFastSmem {
   TileGeom geom[2];
 };
 
-template <typename K, int VB, int THREADS, int IPT, int OCC>
+template <typename K, int VB, int THREADS, int IPT, int OCC, bool PEER = false>
 __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const __grid_constant__ ScatterArgs a) {
   pdl_wait();
-  using SM = StableFastSmem<K, VB, THREADS, IPT>;
+  using SM = StableFastSmem<K, VB, THREADS, IPT, PEER>;
   using V = typename SM::V;
   constexpr int TILE = SM::TILE, WARPS = SM::WARPS;
   constexpr unsigned PRODUCER = THREADS - 1;
@@ -867,7 +876,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
     if (g.tile >= num_tiles) return;
     const uint32_t c = a.tile_cnt[(uint64_t)g.tile * RADIX + tid];
     const uint32_t grp = g.tile / HIST_GROUP;
-    uint64_t gstart = a.bins[(uint64_t)g.seg * RADIX + tid] + a.tile_off[(uint64_t)g.tile * RADIX + tid];
+    uint64_t gstart = (PEER ? 0ull : a.bins[(uint64_t)g.seg * RADIX + tid]) + a.tile_off[(uint64_t)g.tile * RADIX + tid];
     if (g.tile - g.tile_in_seg < grp * HIST_GROUP) gstart += a.carry[(uint64_t)grp * RADIX + tid];
     uint32_t inc = c;
 #pragma unroll
@@ -876,13 +885,26 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
       if (lane >= (unsigned)o) inc += t;
     }
     if (lane == 31) sm.scratch[slot][w] = inc;
+    if (PEER) sm.bsum[PEER ? tid : 0] = 0;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     uint32_t woff = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) woff += ((unsigned)j < w) ? sm.scratch[slot][j] : 0u;
     const uint32_t excl = woff + inc - c;
     sm.excl[slot][tid] = excl;
-    sm.goff[slot][tid] = (uint32_t)gstart - excl;          // n < 2^32: indices wrap correctly in 32 bits
+    if (!PEER) {
+      sm.goff[slot][tid] = (uint32_t)gstart - excl;          // n < 2^32: indices wrap correctly in 32 bits
+    } else {
+      // exchange: the digits of one bucket (digit >> xshift) leave the tile as ONE run, chunk after chunk in the bucket's region of
+      // its destination buffer.  Start of this tile's chunk = bucket start + keys of the bucket in this source's earlier tiles.
+      const uint32_t b = tid >> a.xshift;
+      if (gstart) atomicAdd(&sm.bsum[PEER ? b : 0], (uint32_t)gstart);
+      if ((tid & ((1u << a.xshift) - 1u)) == 0) sm.bexcl[PEER ? b : 0] = (uint16_t)excl;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      sm.goff[slot][tid] = (uint32_t)a.bins[b] + sm.bsum[PEER ? b : 0] - (uint32_t)sm.bexcl[PEER ? b : 0];
+      sm.gdst[PEER ? slot : 0][PEER ? tid : 0] = a.digit_dest[b];
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // bsum / bexcl are reused by the next prepare
+    }
   };
 
   uint32_t tk_a = 0, tk_b = 0;
@@ -902,6 +924,10 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
     for (int i = tid; i < 2 * WARPS * RADIX / 4; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
     uint4* zc = reinterpret_cast<uint4*>(sm.wcnt);
     for (int i = tid; i < WARPS * RADIX / 8; i += THREADS) zc[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (PEER && (int)tid < a.num_parts && tid < (unsigned)MAX_PARTS) {
+    sm.dstk[PEER ? tid : 0] = a.dst_keys[tid];
+    if (VB) sm.dstv[PEER ? tid : 0] = a.dst_vals[tid];
   }
   __syncthreads();
   if (tid < RADIX) prepare(0);
@@ -993,29 +1019,25 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
     const uint32_t* __restrict__ go = sm.goff[slot];
     K* __restrict__ kout = reinterpret_cast<K*>(a.keys_out);
     V* __restrict__ vout = reinterpret_cast<V*>(a.vals_out);
-    if (a.tw_out) {
+    {
       const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+      const bool two = a.tw_out != 0;
 #pragma unroll
       for (int j = 0; j < IPT; ++j) {
         const uint32_t p = j * THREADS + tid;
         if (full || p < cnt) {
-          const K k = st[p];
+          K k = st[p];
           const uint32_t d = digit_of<K>(k, shift, mask);
-          const uint32_t o = go[d] + p;
-          st_global<K>(kout, o, tw_apply_out<K>(k, sg, fl, fp));
-          if (VB) st_global<V>(vout, o, vst[p]);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < IPT; ++j) {
-        const uint32_t p = j * THREADS + tid;
-        if (full || p < cnt) {
-          const K k = st[p];
-          const uint32_t d = digit_of<K>(k, shift, mask);
-          const uint32_t o = go[d] + p;
-          st_global<K>(kout, o, k);
-          if (VB) st_global<V>(vout, o, vst[p]);
+          if (two) k = tw_apply_out<K>(k, sg, fl, fp);
+          if (PEER) {
+            const uint32_t o = go[d] + p, dd = sm.gdst[PEER ? slot : 0][PEER ? d : 0];
+            st_global<K>(reinterpret_cast<K*>(sm.dstk[PEER ? dd : 0]), o, k);
+            if (VB) st_global<V>(reinterpret_cast<V*>(sm.dstv[PEER ? dd : 0]), o, vst[p]);
+          } else {
+            const uint32_t o = go[d] + p;
+            st_global<K>(kout, o, k);
+            if (VB) st_global<V>(vout, o, vst[p]);
+          }
         }
       }
     }

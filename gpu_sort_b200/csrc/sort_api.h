@@ -11,6 +11,8 @@ struct Twiddle;
 // Optional per-kernel timing (b200_prof_enable / b200_prof_report in the C ABI): when enabled, every launch site is
 // bracketed by two CUDA events on the launching stream.  Off by default -- a disabled scope costs one load and a branch.
 extern int g_prof_enabled;
+extern unsigned long long g_prof_launches;      // kernels launched while profiling is enabled (b200_prof_launches)
+inline void note_launch() { if (g_prof_enabled) ++g_prof_launches; }
 void prof_begin(const char* name, cudaStream_t s);
 void prof_end(cudaStream_t s);
 struct ProfScope {
@@ -37,5 +39,13 @@ cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* k
                                  uint64_t n, const Twiddle& tw, int bits, const uint32_t* d_splitters, int num_parts,
                                  const uint64_t* d_local_counts, uint64_t* d_part_offsets, const uint64_t* d_dst_keys, const uint64_t* d_dst_vals,
                                  const uint64_t* d_dst_base, cudaStream_t s);
+
+template <typename K, int VB>
+cudaError_t exchange_hist_impl(void* d_temp, size_t* temp_bytes, const void* kin, uint64_t n, const Twiddle& tw, int bucket_bits, uint64_t* d_hist, cudaStream_t s);
+
+template <typename K, int VB>
+cudaError_t exchange_scatter_impl(void* d_temp, size_t* temp_bytes, const void* kin, const void* vin, uint64_t n, const Twiddle& tw, int bucket_bits,
+                                  const uint64_t* d_matrix, int G, int rank, uint64_t cap, const uint64_t* d_dst_keys, const uint64_t* d_dst_vals,
+                                  uint64_t* d_seg_begin, uint64_t* d_seg_end, uint64_t* d_info, cudaStream_t s);
 
 }  // namespace b200

@@ -39,9 +39,10 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  note_launch();
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 #else
-  kernel<<<grid, block, smem, s>>>(std::forward<Args>(args)...);
+  kernel<<<grid, block, smem, s>>>(std::forward<Args>(args)...); note_launch();
   return cudaSuccess;
 #endif
 }
@@ -126,6 +127,20 @@ inline cudaError_t launch_scatter_stable_fast(const ScatterArgs& a, uint32_t til
   return cudaGetLastError();
 }
 
+template <typename K, int VB>
+inline cudaError_t launch_scatter_exchange(const ScatterArgs& a, uint32_t tiles_hint, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  auto kernel = scatter_stable_fast_kernel<K, VB, C::THREADS, C::IPT, C::OCC, true>;
+  constexpr size_t smem = sizeof(StableFastSmem<K, VB, C::THREADS, C::IPT, true>);
+  static_assert(smem <= 113 * 1024, "two exchange scatter CTAs must fit one SM");
+  static int grid = 0;
+  if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
+  const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
+  ProfScope prof("exchange_scatter", s);
+  launch_k(kernel, g, C::THREADS, smem, s, a);
+  return cudaGetLastError();
+}
+
 template <typename K, int VB, int MODE, bool ORD>
 inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
@@ -138,7 +153,7 @@ inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cud
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
   ProfScope prof(MODE == MODE_RANGE ? "range_partition" : (MODE == MODE_LSB ? "scatter_onesweep" : (ORD ? "scatter_stable" : "scatter")), s);
-  kernel<<<g, C::THREADS, smem, s>>>(a);
+  kernel<<<g, C::THREADS, smem, s>>>(a); note_launch();
   return cudaGetLastError();
 }
 
@@ -605,8 +620,8 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     ha.keys = k0; ha.n = n; ha.num_passes = passes; ha.begin_bit = begin_bit; ha.end_bit = end_bit;
     ha.tw_in = 1; ha.tw = tw; ha.hist = hist;
     const int grid = (int)std::min<uint64_t>((uint64_t)num_sms() * 4, (n + 4095) / 4096);
-    { ProfScope prof("hist_all", s); hist_all_kernel<K><<<grid, HIST_THREADS, 0, s>>>(ha); }
-    { ProfScope prof("scan_bins", s); scan_bins_kernel<<<passes, RADIX, 0, s>>>(hist, 0); }
+    { ProfScope prof("hist_all", s); hist_all_kernel<K><<<grid, HIST_THREADS, 0, s>>>(ha); note_launch(); }
+    { ProfScope prof("scan_bins", s); scan_bins_kernel<<<passes, RADIX, 0, s>>>(hist, 0); note_launch(); }
   }
   const void* src_k = k0; const void* src_v = v0;
   for (int p = 0; p < passes; ++p) {
@@ -781,20 +796,20 @@ cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* k
   if (*temp_bytes < cv.total()) return cudaErrorInvalidValue;
   // part sizes follow from the caller's own top-bits histogram; bins[d] = start of part d (in the shared output, or 0-based
   // inside its own destination buffer + the caller's base when every part has its own buffer)
-  part_offsets_kernel<<<1, 256, 0, s>>>(d_local_counts, 1 << bits, d_splitters, num_parts, d_part_offsets, bins, d_dst_keys ? d_dst_base : nullptr);
+  part_offsets_kernel<<<1, 256, 0, s>>>(d_local_counts, 1 << bits, d_splitters, num_parts, d_part_offsets, bins, d_dst_keys ? d_dst_base : nullptr); note_launch();
   if (n == 0) return cudaGetLastError();
   const int sms = num_sms();
   B200_CHECK(cudaMemsetAsync(ctr, 0, sizeof(MsbCounters), s));
   B200_CHECK(cudaMemsetAsync(seg_hist, 0, RADIX * sizeof(uint32_t), s));
-  msb_init_kernel<<<1, 32, 0, s>>>(seg, ctr, n);
-  scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(seg, &ctr->num_segs[0], tile_base, &ctr->num_tiles[0], max_tiles, &ctr->error, C::TILE);
-  fill_descs_kernel<<<sms * 2, 256, 0, s>>>(seg, tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], descs, C::TILE);
+  msb_init_kernel<<<1, 32, 0, s>>>(seg, ctr, n); note_launch();
+  scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(seg, &ctr->num_segs[0], tile_base, &ctr->num_tiles[0], max_tiles, &ctr->error, C::TILE); note_launch();
+  fill_descs_kernel<<<sms * 2, 256, 0, s>>>(seg, tile_base, &ctr->num_segs[0], &ctr->num_tiles[0], descs, C::TILE); note_launch();
   TileHistArgs ha{};
   ha.keys = kin; ha.descs = descs; ha.num_tiles_ptr = &ctr->num_tiles[0];
   ha.tile_off = tile_off; ha.group_tail = group_tail; ha.group_flag = group_flag; ha.seg_hist = seg_hist;
   ha.shift = KEY_BITS - bits; ha.mask = 0xFFu; ha.tw_in = 1; ha.tw = tw; ha.splitters = d_splitters; ha.num_parts = num_parts;
-  { ProfScope prof("tile_hist", s); tile_hist_kernel<K, true, false><<<(int)std::min<uint32_t>(max_groups, (uint32_t)sms * 4), HIST_THREADS, 0, s>>>(ha); }
-  group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(group_tail, group_flag, carry, &ctr->num_tiles[0]);
+  { ProfScope prof("tile_hist", s); tile_hist_kernel<K, true, false><<<(int)std::min<uint32_t>(max_groups, (uint32_t)sms * 4), HIST_THREADS, 0, s>>>(ha); note_launch(); }
+  group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(group_tail, group_flag, carry, &ctr->num_tiles[0]); note_launch();
   ScatterArgs pa{};
   pa.keys_in = kin; pa.keys_out = kout; pa.vals_in = vin; pa.vals_out = vout;
   pa.descs = descs; pa.num_tiles_ptr = &ctr->num_tiles[0];
@@ -803,6 +818,149 @@ cudaError_t range_partition_impl(void* d_temp, size_t* temp_bytes, const void* k
   pa.tw_in = 1; pa.tw_out = 1; pa.tw = tw;
   pa.splitters = d_splitters; pa.num_parts = num_parts; pa.dst_keys = d_dst_keys; pa.dst_vals = d_dst_vals;
   B200_CHECK((launch_scatter<K, VB, MODE_RANGE, true>(pa, max_tiles, s)));
+  return cudaGetLastError();
+}
+
+// ===============================================================================================================
+// Multi-GPU exchange as level 0 of the sort (gpu_sort_b200/dist.py, ExchangeSorter).
+// Every rank counts the leading 8-bit digit of its keys per tile (exchange_hist: ONE read, the same per-tile histogram pass as a
+// sort level) and publishes its 256 digit totals; from the gathered G x 256 matrix every rank derives the same plan: digits are
+// dealt to the G ranks in contiguous, balanced groups, and inside a destination's receive buffer the digits lie in ascending
+// order, each digit's keys in source-rank order (stable).  exchange_scatter then runs the stable scatter of a sort level whose
+// per-digit destinations are the PEERS' receive buffers (stores over NVLink from the scatter's coalesced write-out): after it,
+// rank D holds level-0 buckets of the global sort, already split, and finishes them with a segmented sort on the remaining
+// bits (b200_segmented_sort with the segment bounds the plan wrote) -- the exchange costs one sweep and replaces one.
+// ===============================================================================================================
+struct ExchangeWorkspace {
+  MsbCounters* ctr; Seg* seg; uint32_t* tile_base; TileDesc* descs; uint32_t* seg_hist; uint32_t* tile_off; uint16_t* tile_cnt;
+  uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; uint64_t* bins; uint8_t* digit_dest; uint32_t max_tiles, max_groups;
+};
+template <typename K, int VB>
+inline void exchange_carve(Carver& cv, uint64_t n, ExchangeWorkspace& w) {
+  using C = Cfg<K, VB>;
+  w.max_tiles = (uint32_t)(n / C::TILE) + 2;
+  w.max_groups = w.max_tiles / HIST_GROUP + 1;
+  w.ctr = cv.take<MsbCounters>(1);
+  w.seg = cv.take<Seg>(2);
+  w.tile_base = cv.take<uint32_t>(4);
+  w.descs = cv.take<TileDesc>(w.max_tiles);
+  w.seg_hist = cv.take<uint32_t>(RADIX);
+  w.tile_off = cv.take<uint32_t>((size_t)w.max_tiles * RADIX);
+  w.tile_cnt = cv.take<uint16_t>((size_t)w.max_tiles * RADIX);
+  w.group_tail = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
+  w.group_flag = cv.take<uint32_t>(w.max_groups);
+  w.carry = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
+  w.bins = cv.take<uint64_t>(RADIX);
+  w.digit_dest = cv.take<uint8_t>(RADIX);
+}
+
+// out[b] = keys of exchange bucket b = sum over the digits (b << xshift) .. ; entries past the last bucket are zero
+static __global__ void __launch_bounds__(RADIX) widen_hist_kernel(const uint32_t* seg_hist, uint64_t* out, int xshift) {
+  const unsigned b = threadIdx.x;
+  unsigned long long sum = 0;
+  if ((b << xshift) < (unsigned)RADIX)
+    for (unsigned d = b << xshift; d < ((b + 1u) << xshift); ++d) sum += seg_hist[d];
+  out[b] = sum;
+}
+
+// info: [0] keys this rank receives, [1] status (0 ok, 1 some rank would receive more than `cap`: nothing is exchanged),
+//       [2] the largest receive count over all ranks, [3] first digit this rank owns, [4] one past the last digit it owns
+static __global__ void __launch_bounds__(RADIX) exchange_plan_kernel(const uint64_t* matrix, int G, int rank, uint64_t cap, uint64_t* bins, uint8_t* digit_dest,
+                                                                     uint64_t* seg_begin, uint64_t* seg_end, uint64_t* info, MsbCounters* ctr) {
+  __shared__ unsigned long long cum[RADIX + 1];      // cum[d] = keys of all ranks with digit < d
+  __shared__ uint32_t bound[MAX_PARTS + 1];          // rank j owns the digits [bound[j], bound[j + 1])
+  const unsigned d = threadIdx.x;
+  unsigned long long tot = 0, before = 0;
+  for (int r = 0; r < G; ++r) { const unsigned long long c = matrix[(size_t)r * RADIX + d]; tot += c; if (r < rank) before += c; }
+  cum[d + 1] = tot;
+  if (d == 0) cum[0] = 0;
+  __syncthreads();
+  if (d == 0) for (int i = 1; i <= RADIX; ++i) cum[i] += cum[i - 1];
+  __syncthreads();
+  const unsigned long long n = cum[RADIX];
+  if (d <= (unsigned)G) {
+    // boundary j: the digit boundary whose cumulative count is closest to j * n / G (ties: the lower one); monotone by construction
+    uint32_t b = d == 0 ? 0u : (d == (unsigned)G ? (uint32_t)RADIX : 0u);
+    if (d > 0 && d < (unsigned)G) {
+      const unsigned long long target = (unsigned long long)(((unsigned __int128)n * d) / (unsigned)G);
+      uint32_t lo = 0, hi = RADIX;                   // first boundary with cum >= target
+      while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cum[mid] >= target) hi = mid; else lo = mid + 1; }
+      b = lo;
+      if (b > 0 && target - cum[b - 1] <= cum[b] - target) b -= 1;
+    }
+    bound[d] = b;
+  }
+  __syncthreads();
+  if (d == 0) for (int j = 1; j <= G; ++j) if (bound[j] < bound[j - 1]) bound[j] = bound[j - 1];
+  __syncthreads();
+  uint32_t dest = 0;
+  for (int j = 1; j < G; ++j) dest += bound[j] <= d ? 1u : 0u;
+  const unsigned long long start = cum[d] - cum[bound[dest]];         // where digit d begins inside its destination's receive buffer
+  bins[d] = start + before;                                           // ... and where this rank's share of it begins
+  digit_dest[d] = (uint8_t)dest;
+  const bool mine = dest == (uint32_t)rank;
+  seg_begin[d] = mine ? start : 0ull;
+  seg_end[d] = mine ? start + tot : 0ull;
+  if (d == 0) {
+    unsigned long long worst = 0;
+    for (int j = 0; j < G; ++j) { const unsigned long long c = cum[bound[j + 1]] - cum[bound[j]]; worst = c > worst ? c : worst; }
+    info[0] = cum[bound[rank + 1]] - cum[bound[rank]];
+    info[1] = worst > cap ? 1ull : 0ull;
+    info[2] = worst; info[3] = bound[rank]; info[4] = bound[rank + 1];
+    if (worst > cap) ctr->num_tiles[0] = 0;                           // the scatter behind this kernel finds nothing to do
+  }
+}
+
+template <typename K, int VB>
+cudaError_t exchange_hist_impl(void* d_temp, size_t* temp_bytes, const void* kin, uint64_t n, const Twiddle& tw, int bucket_bits, uint64_t* d_hist, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  if (n >= (1ull << 32) || bucket_bits < 0 || bucket_bits > 8) return cudaErrorInvalidValue;
+  const int digit_shift = (int)sizeof(K) * 8 - 8;        // ranking digit: the leading 8 bits; bucket = its leading bucket_bits bits
+  Carver cv(d_temp);
+  ExchangeWorkspace w{};
+  exchange_carve<K, VB>(cv, n, w);
+  if (d_temp == nullptr) { *temp_bytes = std::max<size_t>(cv.total(), 256); return cudaSuccess; }
+  if (*temp_bytes < cv.total()) return cudaErrorInvalidValue;
+  const int sms = num_sms();
+  B200_CHECK(cudaMemsetAsync(w.ctr, 0, sizeof(MsbCounters), s));
+  B200_CHECK(cudaMemsetAsync(w.seg_hist, 0, RADIX * sizeof(uint32_t), s));
+  msb_init_kernel<<<1, 32, 0, s>>>(w.seg, w.ctr, n); note_launch();
+  scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(w.seg, &w.ctr->num_segs[0], w.tile_base, &w.ctr->num_tiles[0], w.max_tiles, &w.ctr->error, C::TILE); note_launch();
+  fill_descs_kernel<<<sms * 2, 256, 0, s>>>(w.seg, w.tile_base, &w.ctr->num_segs[0], &w.ctr->num_tiles[0], w.descs, C::TILE); note_launch();
+  TileHistArgs ha{};
+  ha.keys = kin; ha.descs = w.descs; ha.num_tiles_ptr = &w.ctr->num_tiles[0];
+  ha.tile_off = w.tile_off; ha.group_tail = w.group_tail; ha.group_flag = w.group_flag; ha.seg_hist = w.seg_hist; ha.tile_cnt = w.tile_cnt;
+  const int nb = std::min(8, (int)sizeof(K) * 8 - digit_shift);
+  ha.shift = digit_shift; ha.mask = (1u << nb) - 1u; ha.tw_in = 1; ha.tw = tw;
+  ha.ticket = &w.ctr->part_ticket[0];
+  { ProfScope prof("tile_hist", s); tile_hist_kernel<K, false, false><<<(int)std::min<uint32_t>(w.max_groups, (uint32_t)sms * 4), HIST_THREADS, 0, s>>>(ha); note_launch(); }
+  group_carry_kernel<<<RADIX / 32, CARRY_WARPS * 32, 0, s>>>(w.group_tail, w.group_flag, w.carry, &w.ctr->num_tiles[0]); note_launch();
+  widen_hist_kernel<<<1, RADIX, 0, s>>>(w.seg_hist, d_hist, 8 - bucket_bits); note_launch();
+  return cudaGetLastError();
+}
+
+template <typename K, int VB>
+cudaError_t exchange_scatter_impl(void* d_temp, size_t* temp_bytes, const void* kin, const void* vin, uint64_t n, const Twiddle& tw, int bucket_bits,
+                                  const uint64_t* d_matrix, int G, int rank, uint64_t cap, const uint64_t* d_dst_keys, const uint64_t* d_dst_vals,
+                                  uint64_t* d_seg_begin, uint64_t* d_seg_end, uint64_t* d_info, cudaStream_t s) {
+  using C = Cfg<K, VB>;
+  if (n >= (1ull << 32) || G < 1 || G > MAX_PARTS || rank < 0 || rank >= G || cap >= (1ull << 32) || bucket_bits < 0 || bucket_bits > 8) return cudaErrorInvalidValue;
+  const int digit_shift = (int)sizeof(K) * 8 - 8;
+  Carver cv(d_temp);
+  ExchangeWorkspace w{};
+  exchange_carve<K, VB>(cv, n, w);
+  if (d_temp == nullptr) { *temp_bytes = std::max<size_t>(cv.total(), 256); return cudaSuccess; }
+  if (*temp_bytes < cv.total()) return cudaErrorInvalidValue;
+  exchange_plan_kernel<<<1, RADIX, 0, s>>>(d_matrix, G, rank, cap, w.bins, w.digit_dest, d_seg_begin, d_seg_end, d_info, w.ctr); note_launch();
+  if (n == 0) return cudaGetLastError();
+  const int nb = std::min(8, (int)sizeof(K) * 8 - digit_shift);
+  ScatterArgs pa{};
+  pa.keys_in = kin; pa.vals_in = vin; pa.keys_out = nullptr; pa.vals_out = nullptr;
+  pa.descs = w.descs; pa.num_tiles_ptr = &w.ctr->num_tiles[0];
+  pa.bins = w.bins; pa.tile_off = w.tile_off; pa.carry = w.carry; pa.tile_cnt = w.tile_cnt;
+  pa.shift = digit_shift; pa.mask = (1u << nb) - 1u; pa.tw_in = 1; pa.tw_out = 1; pa.tw = tw;
+  pa.num_parts = G; pa.dst_keys = d_dst_keys; pa.dst_vals = d_dst_vals; pa.digit_dest = w.digit_dest; pa.xshift = 8 - bucket_bits;
+  B200_CHECK((launch_scatter_exchange<K, VB>(pa, w.max_tiles, s)));
   return cudaGetLastError();
 }
 

@@ -152,9 +152,40 @@ int grid_for(uint64_t n, int threads) {
   return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
+// Store-bandwidth probe for peer (NVLink) or local memory: writes `bytes` to dst in one of three patterns.
+//   mode 0: every warp instruction stores 128 contiguous bytes (4 bytes per lane)
+//   mode 1: every warp instruction stores 512 contiguous bytes (16 bytes per lane)
+//   mode 2: 4-byte lanes, but consecutive `chunk`-byte pieces go to pseudo-random `chunk`-aligned places (a scatter's runs)
+//   mode 3: 16-byte lanes, pieces of `chunk` bytes at pseudo-random places
+__global__ void store_probe_kernel(uint32_t* dst, uint64_t bytes, int mode, uint32_t chunk) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
+  if (mode == 0) {
+    for (uint64_t i = t; i < bytes / 4; i += nt) dst[i] = (uint32_t)i;
+  } else if (mode == 1) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (uint64_t i = t; i < bytes / 16; i += nt) d4[i] = make_uint4((uint32_t)i, 1, 2, 3);
+  } else {
+    const uint64_t nchunks = bytes / chunk;            // power of two expected
+    const uint32_t per = chunk / (mode == 2 ? 4 : 16);   // lanes per chunk
+    const uint64_t units = bytes / (mode == 2 ? 4 : 16);
+    for (uint64_t i = t; i < units; i += nt) {
+      const uint64_t c = i / per, o = i % per;
+      const uint64_t pc = (c * 0x9E3779B97F4A7C15ull >> 20) & (nchunks - 1);     // scrambled chunk index (bijective enough for a bandwidth probe)
+      if (mode == 2) dst[pc * (chunk / 4) + o] = (uint32_t)i;
+      else reinterpret_cast<uint4*>(dst)[pc * (chunk / 16) + o] = make_uint4((uint32_t)i, 1, 2, 3);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+B200_API int b200_util_store_probe(void* dst, uint64_t bytes, int mode, uint32_t chunk, int grid, int block, b200_stream_t stream) {
+  store_probe_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint32_t*>(dst), bytes, mode, chunk);
+  return (int)cudaGetLastError();
+}
+
 
 int b200_util_generate_keys(void* d_keys, uint64_t num_items, uint64_t start_index, uint64_t total_items, int key_bits,
                             uint64_t seed, int dist, uint64_t param, b200_stream_t stream) {

@@ -222,9 +222,17 @@ class DistSorter:
         self.pairs = value_dtype is not None
         self.stable = self.pairs if stable is None else stable
         self.n_local = n_local
-        self.cap = int(n_local * slack) + 4096
-        dev = torch.device("cuda", torch.cuda.current_device())
+        self.key_dtype, self.value_dtype = key_dtype, value_dtype
         self.fused = fused and self.G > 1
+        self._alloc(int(n_local * slack) + 4096)
+
+    def _alloc(self, cap: int):
+        """(Re)allocates everything sized by the receive capacity.  Collective when fused (symmetric-memory rendezvous): every
+        rank calls it with the same capacity -- sort() derives it from the all-gathered count matrix, identical on all ranks."""
+        gs, group, n_local, bits = self.gs, self.group, self.n_local, self.bits
+        key_dtype, value_dtype = self.key_dtype, self.value_dtype
+        self.cap = cap
+        dev = torch.device("cuda", torch.cuda.current_device())
         self.hk = self.hv = None
         if self.fused:
             try:
@@ -252,8 +260,9 @@ class DistSorter:
             self.recv_v = None
         self.alt_k = torch.empty(self.cap, dtype=key_dtype, device=dev)
         self.alt_v = torch.empty(self.cap, dtype=value_dtype, device=dev) if self.pairs else None
-        self.counts = torch.empty(1 << bits, dtype=torch.int64, device=dev)
-        self.offs = torch.zeros(self.G + 1, dtype=torch.int64, device=dev)
+        if not hasattr(self, "counts"):          # (kept across a re-allocation: sort() grows the buffers after the histogram is taken)
+            self.counts = torch.empty(1 << bits, dtype=torch.int64, device=dev)
+            self.offs = torch.zeros(self.G + 1, dtype=torch.int64, device=dev)
         vb = gs._value_bytes(self.recv_v)
         self.vb = vb
         nb = ctypes.c_size_t(0)
@@ -306,8 +315,11 @@ class DistSorter:
         lo = (int(host[G * G + rank - 1]) if rank > 0 else 0) << (kbits - bits)
         hi = (((int(host[G * G + rank]) if rank < G - 1 else (1 << bits)) << (kbits - bits)) - 1) if G > 1 else (1 << kbits) - 1
         end_bit = max((lo ^ max(hi, lo)).bit_length(), 1)
-        if n_recv > self.cap:
-            raise RuntimeError(f"rank {rank}: {n_recv} keys to receive exceed the receive capacity {self.cap} (key range too skewed for range partitioning)")
+        worst = int(matrix.sum(axis=0).max())
+        if worst > self.cap:
+            # a key range heavier than the receive capacity (heavy duplicates: one bucket cannot be split by key range): tolerated as
+            # imbalance (reported in info) -- every rank sees the same matrix, so all of them grow their buffers together
+            self._alloc(int(worst * 1.02) + 4096)
         nb = ctypes.c_size_t(self.part_temp.numel())
         if self.fused:
             self.hk.barrier()                                        # every peer is done with the previous contents of its receive buffer
@@ -351,3 +363,199 @@ class DistSorter:
             gs.prof_enable(False)
             info["phases_ms"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 3) for i in range(1, len(marks))}
         return sk, sv, info
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The default multi-GPU path: the exchange IS level 0 of the sort
+# ----------------------------------------------------------------------------------------------------------------
+def exchange_plan(matrix: np.ndarray, cap: Optional[int] = None):
+    """Host restatement of exchange_plan_kernel (csrc/sort_impl.cuh), used by the CPU tests and to cross-check the device plan.
+    matrix[r][d] = keys of source rank r whose leading digit is d.  Returns (bound, start, ok): rank j owns the digits
+    [bound[j], bound[j+1]); start[d] = index of digit d inside its destination's receive buffer; ok = nobody exceeds `cap`."""
+    m = np.asarray(matrix, dtype=np.uint64)
+    G, R = m.shape
+    tot = m.sum(axis=0)
+    cum = np.concatenate([[0], np.cumsum(tot, dtype=np.uint64)]).astype(np.uint64)
+    n = int(cum[-1])
+    bound = [0]
+    for j in range(1, G):
+        target = (n * j) // G
+        b = int(np.searchsorted(cum, np.uint64(target), side="left"))
+        if b > 0 and target - int(cum[b - 1]) <= int(cum[b]) - target:
+            b -= 1
+        bound.append(max(b, bound[-1]))
+    bound.append(R)
+    start = np.zeros(R, dtype=np.uint64)
+    for j in range(G):
+        for d in range(bound[j], bound[j + 1]):
+            start[d] = cum[d] - cum[bound[j]]
+    recv = [int(cum[bound[j + 1]] - cum[bound[j]]) for j in range(G)]
+    return bound, start, (cap is None or max(recv) <= cap), recv
+
+
+def default_xbits(n_total: int, G: int) -> int:
+    """Exchange buckets = leading xbits bits of the key: enough to deal whole buckets to the ranks (2 extra bits when G is not a
+    power of two), few enough that a scatter tile's run per bucket is long (NVLink wants >= 128-byte pieces), and such that two
+    8-bit levels of the local finish leave ~4096-key buckets: log2(total keys) - 16 - 12."""
+    total_bits = max(int(np.ceil(np.log2(max(n_total, 2)))), 1)
+    need = int(np.ceil(np.log2(G))) + (0 if (G & (G - 1)) == 0 else 2)
+    return int(min(8, max(need, total_bits - 28)))
+
+
+def exchange_sort(keys: torch.Tensor, vals: Optional[torch.Tensor] = None, group=None, xbits: Optional[int] = None, ops=None, key_bits: int = 32):
+    """The exchange-as-level-0 sort with the collectives spelled out (all_gather of the bucket counts, all_to_all of the parts):
+    the same plan ExchangeSorter executes on the GPUs with the scatter fused into the exchange, runnable under gloo with a test
+    double for the three device operations (`ops.bucket_hist`, `ops.bucket_partition`, `ops.local_sort`)."""
+    G = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if xbits is None:
+        n_all = torch.tensor([keys.numel()], dtype=torch.int64)
+        if G > 1:
+            dist.all_reduce(n_all, group=group)
+        xbits = default_xbits(int(n_all.item()), G)
+    hist = ops.bucket_hist(keys, xbits, key_bits)                              # int64[256]
+    gathered = [torch.empty_like(hist) for _ in range(G)]
+    if G > 1:
+        dist.all_gather(gathered, hist, group=group)
+    else:
+        gathered = [hist]
+    matrix = np.stack([g.cpu().numpy() for g in gathered]).astype(np.int64)   # [src][bucket]
+    bound, start, ok, recv_counts = exchange_plan(matrix)
+    pk, pv, send = ops.bucket_partition(keys, vals, xbits, bound, key_bits)    # stable, ordered by destination then bucket
+    recv = [int(matrix[r, bound[rank]:bound[rank + 1]].sum()) for r in range(G)]
+    n_recv = sum(recv)
+    rk = torch.empty(max(n_recv, 1), dtype=keys.dtype)[:n_recv]
+    rv = torch.empty(max(n_recv, 1), dtype=vals.dtype)[:n_recv] if vals is not None else None
+    if G > 1:
+        dist.all_to_all_single(rk, pk, output_split_sizes=recv, input_split_sizes=send, group=group)
+        if vals is not None:
+            dist.all_to_all_single(rv, pv, output_split_sizes=recv, input_split_sizes=send, group=group)
+    else:
+        rk.copy_(pk)
+        if vals is not None:
+            rv.copy_(pv)
+    sk, sv = ops.local_sort(rk, rv, n_recv, True) if n_recv else (rk, rv)
+    return sk, sv, {"count": n_recv, "bound": bound, "xbits": xbits, "imbalance": max(recv_counts) / max(sum(recv_counts) / G, 1), "matrix": matrix}
+
+
+class ExchangeSorter:
+    """Multi-GPU sort of 4-/8-byte keys (+ values), one process per GPU, everything allocated up front, NO host read-back
+    inside sort():
+
+        count   : per-tile histogram of the leading 8-bit digit, one read of the keys        b200_exchange_hist
+        gather  : all_gather of every rank's 256 digit totals (G x 2 KB)                      NCCL
+        scatter : every rank derives the same plan on the device (digits dealt to ranks in contiguous balanced groups) and
+                  runs the stable scatter of a sort level whose destinations are the PEERS' receive buffers
+                  (symmetric memory, stores over NVLink from the scatter's coalesced write-out) b200_exchange_scatter
+        finish  : each rank now holds level-0 buckets of the global sort: segmented sort on the remaining bits
+                                                                                               b200_segmented_sort
+    Stable for pairs: inside a digit the keys arrive in source-rank order, the scatter and the segmented sort are stable, so
+    the global result equals ONE stable sort of the concatenated input.  The received count, the status word (1 = a rank
+    would receive more than its capacity: nothing was exchanged, use DistSorter's key-range path) and the largest receive
+    count live in `self.info` on the device; result() reads them back.
+    """
+
+    def __init__(self, n_local: int, key_dtype=torch.int32, value_dtype=None, group=None, slack: float = 1.15, key_type: Optional[int] = None, xbits: Optional[int] = None):
+        import gpu_sort_b200 as gs
+        import torch.distributed._symmetric_memory as symm
+        self.gs, self.group = gs, group
+        self.G, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.kt = key_type if key_type is not None else gs._TORCH_KEY[key_dtype]
+        self.kbits = gs.KEY_BYTES[self.kt] * 8
+        self.pairs = value_dtype is not None
+        self.n_local = n_local
+        self.cap = int(n_local * slack) + 4096
+        dev = torch.device("cuda", torch.cuda.current_device())
+        gname = (group or dist.group.WORLD).group_name
+        self.recv_k = symm.empty(self.cap, dtype=key_dtype, device=dev)
+        self.hk = symm.rendezvous(self.recv_k, gname)
+        ptrs_k = [int(p) for p in self.hk.buffer_ptrs]
+        ptrs_v = [0] * self.G
+        self.recv_v = None
+        if self.pairs:
+            self.recv_v = symm.empty(self.cap, dtype=value_dtype, device=dev)
+            self.hv = symm.rendezvous(self.recv_v, gname)
+            ptrs_v = [int(p) for p in self.hv.buffer_ptrs]
+        self.dst_k = torch.tensor(ptrs_k, dtype=torch.int64, device=dev)
+        self.dst_v = torch.tensor(ptrs_v, dtype=torch.int64, device=dev)
+        self.alt_k = torch.empty(self.cap, dtype=key_dtype, device=dev)
+        self.alt_v = torch.empty(self.cap, dtype=value_dtype, device=dev) if self.pairs else None
+        self.hist = torch.zeros(256, dtype=torch.int64, device=dev)
+        self.matrix = torch.zeros(self.G * 256, dtype=torch.int64, device=dev)
+        self.seg_begin = torch.zeros(256, dtype=torch.int64, device=dev)
+        self.seg_end = torch.zeros(256, dtype=torch.int64, device=dev)
+        self.info = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.vb = gs._value_bytes(self.recv_v)
+        # exchange buckets = leading xbits bits of the key: enough of them to deal whole buckets to the ranks, few enough that a
+        # scatter tile's run per bucket is long (NVLink wants >= 128-byte pieces), and such that two 8-bit levels of the local
+        # finish leave buckets that fit on chip (~4096 keys): xbits = log2(total keys) - 16 - 12
+        self.xbits = default_xbits(n_local * self.G, self.G) if xbits is None else int(xbits)
+        self.shift = self.kbits - self.xbits
+        nb = ctypes.c_size_t(0)
+        gs._check(gs.lib.b200_exchange_hist(None, ctypes.byref(nb), None, n_local, self.kt, self.vb, self.xbits, None, None), "b200_exchange_hist(size query)")
+        self.x_temp = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        tb = ctypes.c_size_t(0)
+        gs._check(gs.lib.b200_segmented_sort(None, ctypes.byref(tb), None, None, None, None, None, self.cap, 256, None, None, 8, self.kt, self.vb, 0, self.shift, 0, 1, None),
+                  "b200_segmented_sort(size query)")
+        self.s_temp = torch.empty(tb.value, dtype=torch.uint8, device=dev)
+        self._last = None
+        self._fallback = None
+
+    def sort(self, keys: torch.Tensor, vals: Optional[torch.Tensor] = None, profile: bool = False):
+        """Enqueues the whole sort on the current stream; returns nothing the host has to wait for.  result() hands out the tensors."""
+        gs, G = self.gs, self.G
+        n = keys.numel()
+        stream = gs._stream(None)
+        marks = []
+
+        def mark(name):
+            if profile:
+                e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e))
+        if profile:
+            gs.prof_enable(True)
+        mark("start")
+        nb = ctypes.c_size_t(self.x_temp.numel())
+        gs._check(gs.lib.b200_exchange_hist(gs._ptr(self.x_temp), ctypes.byref(nb), gs._ptr(keys), n, self.kt, self.vb, self.xbits, gs._ptr(self.hist), stream),
+                  "b200_exchange_hist")
+        mark("count")
+        if G > 1:
+            dist.all_gather_into_tensor(self.matrix, self.hist, group=self.group)
+        else:
+            self.matrix.copy_(self.hist)
+        mark("gather")
+        self.hk.barrier()                                            # every peer is done with the previous contents of its receive buffer
+        mark("barrier0")
+        gs._check(gs.lib.b200_exchange_scatter(gs._ptr(self.x_temp), ctypes.byref(nb), gs._ptr(keys), gs._ptr(vals), n, self.kt, self.vb, self.xbits,
+                                               gs._ptr(self.matrix), G, self.rank, self.cap, gs._ptr(self.dst_k), gs._ptr(self.dst_v),
+                                               gs._ptr(self.seg_begin), gs._ptr(self.seg_end), gs._ptr(self.info), stream), "b200_exchange_scatter")
+        mark("scatter")
+        self.hk.barrier()                                            # all peers' stores have landed
+        mark("barrier1")
+        dk = gs.DoubleBuffer(self.recv_k, self.alt_k)
+        dv = gs.DoubleBuffer(self.recv_v, self.alt_v) if self.pairs else None
+        gs.DeviceSegmentedRadixSort._run(self.s_temp, dk, dv, self.cap, 256, self.seg_begin, self.seg_end, 0, self.shift, False, None, self.kt)
+        mark("finish")
+        self._last = (dk.Current(), dv.Current() if self.pairs else None, keys, vals)
+        if profile:
+            torch.cuda.synchronize()
+            launches = gs.prof_launches()
+            rep = gs.prof_report()
+            self.profile = {"kernels_ms": {k: round(v[1], 3) for k, v in rep.items()}, "launches": launches,
+                            "phases_ms": {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 3) for i in range(1, len(marks))}}
+            gs.prof_enable(False)
+
+    def result(self):
+        """(sorted_keys, sorted_values, info) of the last sort(); synchronises (one 64-byte read-back).  If the digit-aligned plan
+        could not balance the ranks within the receive capacity, the sort is redone through DistSorter's key-range path."""
+        sk, sv, keys, vals = self._last
+        host = self.info.cpu().numpy()
+        n_recv, status, worst = int(host[0]), int(host[1]), int(host[2])
+        info = {"count": n_recv, "status": status, "imbalance": worst / max(self.n_local, 1), "fused": True, "path": "exchange-as-level-0",
+                "digits": (int(host[3]), int(host[4]))}
+        if status != 0:
+            if self._fallback is None:
+                self._fallback = DistSorter(self.n_local, keys.dtype, vals.dtype if vals is not None else None, self.group, key_type=self.kt)
+            k, v, finfo = self._fallback.sort(keys, vals)
+            finfo["path"] = "key-range fallback"; finfo["status"] = status
+            return k, v, finfo
+        return sk[:n_recv], (sv[:n_recv] if sv is not None else None), info

@@ -174,6 +174,25 @@ B200_API int b200_range_partition_to(void* d_temp, size_t* temp_bytes,
                             uint64_t* d_part_offsets, const uint64_t* d_dst_keys, const uint64_t* d_dst_values,
                             const uint64_t* d_dst_base, b200_stream_t stream);
 
+/* The exchange as LEVEL 0 of the sort (the default multi-GPU path, gpu_sort_b200/dist.py ExchangeSorter): every rank counts its
+ * keys per tile and per leading 8-bit digit of the transformed key -- b200_exchange_hist, ONE read -- and reports how many fall
+ * into each of the 2^bucket_bits exchange BUCKETS (bucket = leading bucket_bits bits, 0 <= bucket_bits <= 8; d_hist = uint64[256],
+ * entries past 2^bucket_bits are zero).  The caller all-gathers the G x 256 matrix, and b200_exchange_scatter derives the same
+ * plan on every rank (buckets dealt to the ranks in contiguous balanced groups; inside a destination buffer buckets ascend, each
+ * bucket's keys in source-rank order) and runs the stable scatter whose per-bucket destinations are the peers' receive buffers.
+ * Afterwards rank r holds whole buckets of the global sort: d_seg_begin / d_seg_end (uint64[256], device) bound them inside its
+ * receive buffer, ready for b200_segmented_sort with end_bit = key bits - bucket_bits.  d_info (uint64[8], device): [0] keys received by this rank, [1] status
+ * (1: some rank would receive more than `capacity` keys -- nothing was written, use the key-range partition above), [2] the
+ * largest receive count, [3]/[4] first / one-past-last digit this rank owns.  Both calls share d_temp (same size, contents kept
+ * from the first call to the second).  The caller synchronises the ranks around the scatter like b200_range_partition_to. */
+B200_API int b200_exchange_hist(void* d_temp, size_t* temp_bytes, const void* d_keys_in, uint64_t num_items, int key_type,
+                       int value_bytes, int bucket_bits, uint64_t* d_hist, b200_stream_t stream);
+B200_API int b200_exchange_scatter(void* d_temp, size_t* temp_bytes, const void* d_keys_in, const void* d_values_in,
+                          uint64_t num_items, int key_type, int value_bytes, int bucket_bits,
+                          const uint64_t* d_count_matrix, int num_ranks, int rank, uint64_t capacity,
+                          const uint64_t* d_dst_keys, const uint64_t* d_dst_values,
+                          uint64_t* d_seg_begin, uint64_t* d_seg_end, uint64_t* d_info, b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Benchmark / test utilities that run on the device (synthetic inputs of SURVEY.md section 8d and size-independent
  * result checks).  Same generator as oracle/radix_oracle.c (oracle_gen_key), so CPU and GPU see identical inputs.
@@ -198,6 +217,8 @@ B200_API int b200_util_check(const void* d_keys, const void* d_values, uint64_t 
  * ------------------------------------------------------------------------------------------------------------------ */
 B200_API int b200_prof_enable(int enable);
 B200_API int b200_prof_report(char* buf, size_t buf_bytes);
+/* Kernels the library launched since b200_prof_enable(1) (every launch site counts itself while profiling is on). */
+B200_API unsigned long long b200_prof_launches(void);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,19 @@ class NumpyOps:
         offs = np.concatenate([[0], np.cumsum(np.bincount(dest, minlength=len(splitters) + 1))]).astype(np.int64)
         return keys[torch.from_numpy(order)], (vals[torch.from_numpy(order)] if vals is not None else None), torch.from_numpy(offs)
 
+    def bucket_hist(self, keys, xbits, key_bits=32):
+        k = keys.numpy().view(np.uint32)
+        b = (k >> np.uint32(32 - xbits)).astype(np.int64) if xbits else np.zeros(k.size, dtype=np.int64)
+        return torch.from_numpy(np.bincount(b, minlength=256).astype(np.int64))
+
+    def bucket_partition(self, keys, vals, xbits, bound, key_bits=32):
+        k = keys.numpy().view(np.uint32)
+        b = (k >> np.uint32(32 - xbits)).astype(np.int64) if xbits else np.zeros(k.size, dtype=np.int64)
+        order = torch.from_numpy(np.argsort(b, kind="stable"))            # by bucket = by destination then bucket (destinations own bucket ranges)
+        cnt = np.bincount(b, minlength=256)
+        send = [int(cnt[bound[j]:bound[j + 1]].sum()) for j in range(len(bound) - 1)]
+        return keys[order], (vals[order] if vals is not None else None), send
+
     def local_sort(self, keys, vals, n, stable):
         order = torch.from_numpy(np.argsort(keys.numpy().view(np.uint32), kind="stable"))
         return keys[order], (vals[order] if vals is not None else None)
@@ -117,3 +130,63 @@ def test_choose_splitters_properties():
     m = np.array([[5, 0], [7, 0]])
     assert gd.receive_layout(m, 0) == ([5, 0], [5, 7], 12) and gd.receive_layout(m, 1) == ([7, 0], [0, 0], 0)
     assert gd.imbalance(m) == 2.0
+
+
+def _worker_exchange(rank, world, port, total, dist_name, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gpu_sort_b200 import dist as gd
+        k = _gen(total, dist_name)
+        lo, hi = rank * total // world, (rank + 1) * total // world
+        keys = torch.from_numpy(k[lo:hi].view(np.int32).copy())
+        vals = torch.arange(lo, hi, dtype=torch.int32)
+        sk, sv, info = gd.exchange_sort(keys, vals, ops=NumpyOps(), xbits=6)
+        q.put((rank, sk.numpy().view(np.uint32).copy(), sv.numpy().view(np.uint32).copy(), info["count"], info["bound"], info["imbalance"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dist_name", [(2, "uniform"), (3, "uniform"), (2, "lowent"), (2, "constant"), (3, "sorted")])
+def test_exchange_as_level_0_equals_one_stable_sort(world, dist_name):
+    """The default multi-GPU plan (buckets dealt to ranks in contiguous balanced groups, bucket-major receive layout in source-rank
+    order, segmented finish): same host logic as ExchangeSorter, collectives under gloo, device operations by the numpy double."""
+    total = 50000 + 11
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_exchange, args=(r, world, port, total, dist_name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    k = _gen(total, dist_name)
+    order = np.argsort(k, kind="stable")
+    got_k = np.concatenate([o[1] for o in out]); got_v = np.concatenate([o[2] for o in out])
+    assert np.array_equal(got_k, k[order])
+    assert np.array_equal(got_v, order.astype(np.uint32))          # values = global indices: identical to ONE stable sort
+    assert sum(o[3] for o in out) == total
+    assert all(o[4] == out[0][4] for o in out)                     # every rank derived the same plan
+    if dist_name == "uniform":
+        assert out[0][5] < 1.2
+
+
+def test_exchange_plan_properties():
+    from gpu_sort_b200 import dist as gd
+    rng = np.random.default_rng(3)
+    for G in (1, 2, 3, 8):
+        m = np.zeros((G, 256), dtype=np.int64)
+        m[:, :64] = rng.integers(0, 1000, size=(G, 64))
+        bound, start, ok, recv = gd.exchange_plan(m, cap=None)
+        assert bound[0] == 0 and bound[-1] == 256 and all(bound[i] <= bound[i + 1] for i in range(G))
+        assert sum(recv) == int(m.sum())
+        for j in range(G):            # inside a destination the buckets lie back to back in ascending order
+            run = 0
+            for d in range(bound[j], bound[j + 1]):
+                assert int(start[d]) == run
+                run += int(m[:, d].sum())
+            assert run == recv[j]
+    m = np.zeros((2, 256), dtype=np.int64); m[:, 5] = 1000          # one heavy bucket: cannot be balanced, reported through ok
+    bound, start, ok, recv = gd.exchange_plan(m, cap=1200)
+    assert not ok and max(recv) == 2000
