@@ -10,6 +10,8 @@
 #define GPU_RADIX_SORT_H_          /* the reference header's guard (msb/src/sort/gpu_radix_sort.h:1-2) */
 #endif
 #include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 #include <cub/util_type.cuh>          // cub::NullType, the reference's keys-only marker (any CUB provides it)
 #include "../../b200sort.h"
@@ -51,6 +53,9 @@ template <> struct key_type_of<unsigned long> { static constexpr int value = siz
 template <> struct key_type_of<long long> { static constexpr int value = B200_KEY_I64; };
 template <> struct key_type_of<long> { static constexpr int value = sizeof(long) == 8 ? B200_KEY_I64 : B200_KEY_I32; };
 template <> struct key_type_of<double> { static constexpr int value = B200_KEY_F64; };
+inline void die_on_error(int rc, const char* what) {
+  if (rc != 0) { fprintf(stderr, "%s failed: %s\n", what, b200_error_string(rc)); exit(-1); }
+}
 template <typename V> struct value_bytes_of { static constexpr int value = (int)sizeof(V); };
 template <> struct value_bytes_of<cub::NullType> { static constexpr int value = 0; };
 }  // namespace b200shim
@@ -72,10 +77,11 @@ RDXSRT_SortedSequence<KeyT, ValueT> rdxsrt_unstable_sort(KeyT* dev_keys, ValueT*
   constexpr int vb = b200shim::value_bytes_of<ValueT>::value;
   void* ok = dev_keys; void* ov = (void*)dev_values;
   size_t bytes = pre_allocated_dm ? pre_allocated_dm->bytes : 0;
-  b200_msb_sort(dev_keys, vb ? (void*)dev_values : nullptr, (uint64_t)key_count, dev_sorted_keys_out, vb ? (void*)dev_sorted_values_out : nullptr,
-                b200shim::key_type_of<KeyT>::value, vb, pre_allocated_dm ? pre_allocated_dm->workspace : nullptr,
-                pre_allocated_dm ? &bytes : nullptr, (b200_stream_t)cstrm_extsrt, &ok, &ov);
-  cudaStreamSynchronize(cstrm_extsrt);
+  const int rc = b200_msb_sort(dev_keys, vb ? (void*)dev_values : nullptr, (uint64_t)key_count, dev_sorted_keys_out, vb ? (void*)dev_sorted_values_out : nullptr,
+                               b200shim::key_type_of<KeyT>::value, vb, pre_allocated_dm ? pre_allocated_dm->workspace : nullptr,
+                               pre_allocated_dm ? &bytes : nullptr, (b200_stream_t)cstrm_extsrt, &ok, &ov);
+  b200shim::die_on_error(rc, "rdxsrt_unstable_sort");          // the reference exit(-1)s on failure (gpu_radix_sort.h:397-400); never return unsorted data
+  b200shim::die_on_error((int)cudaStreamSynchronize(cstrm_extsrt), "rdxsrt_unstable_sort (synchronize)");
   RDXSRT_SortedSequence<KeyT, ValueT> r;
   r.sorted_keys = (KeyT*)ok; r.sorted_values = (ValueT*)ov;
   return r;
@@ -84,9 +90,10 @@ RDXSRT_SortedSequence<KeyT, ValueT> rdxsrt_unstable_sort(KeyT* dev_keys, ValueT*
 // Host-pointer wrappers (gpu_radix_sort.h:510-541, 543-587).
 template <typename KeyT>
 void rdxsrt_unstable_sort_keys(KeyT* keys, unsigned long long key_count, KeyT* sorted_keys_out) {
-  b200_msb_sort_host(keys, nullptr, key_count, sorted_keys_out, nullptr, b200shim::key_type_of<KeyT>::value, 0);
+  b200shim::die_on_error(b200_msb_sort_host(keys, nullptr, key_count, sorted_keys_out, nullptr, b200shim::key_type_of<KeyT>::value, 0), "rdxsrt_unstable_sort_keys");
 }
 template <typename KeyT, typename ValueT>
 void rdxsrt_unstable_sort_pairs(KeyT* keys, ValueT* values, unsigned long long key_count, KeyT* sorted_keys_out, ValueT* sorted_values_out) {
-  b200_msb_sort_host(keys, values, key_count, sorted_keys_out, sorted_values_out, b200shim::key_type_of<KeyT>::value, (int)sizeof(ValueT));
+  b200shim::die_on_error(b200_msb_sort_host(keys, values, key_count, sorted_keys_out, sorted_values_out, b200shim::key_type_of<KeyT>::value, (int)sizeof(ValueT)),
+                         "rdxsrt_unstable_sort_pairs");
 }
