@@ -68,6 +68,12 @@ def _load():
         lib.b200_exchange_hist.argtypes = [vp, P(sz), vp, u64, i32, i32, i32, vp, vp]
         lib.b200_exchange_scatter.restype = i32
         lib.b200_exchange_scatter.argtypes = [vp, P(sz), vp, vp, u64, i32, i32, i32, vp, i32, i32, u64, vp, vp, vp, vp, vp, vp]
+    if hasattr(lib, "b200_sort_status"):
+        lib.b200_sort_status.restype = i32
+        lib.b200_sort_status.argtypes = [vp, vp, P(i32)]
+        lib.b200_set_key_range_probe.restype = i32
+        lib.b200_set_key_range_probe.argtypes = [i32]
+        lib.b200_host_cache_release.restype = i32
     lib.b200_msb_sort_host.restype = i32
     lib.b200_msb_sort_host.argtypes = [vp, vp, u64, vp, vp, i32, i32]
     lib.b200_lsb_sort_host.restype = i32
@@ -370,6 +376,18 @@ def check(keys: torch.Tensor, values: Optional[torch.Tensor] = None, descending=
 def prof_enable(on: bool = True):
     """Bracket every kernel launch of the library with CUDA events (b200_prof_enable)."""
     _check(lib.b200_prof_enable(int(on)), "b200_prof_enable")
+
+
+def sort_status(d_temp: torch.Tensor, stream=None) -> int:
+    """Device-side status word of the last sort that used `d_temp` (b200_sort_status); 0 = ok.  Synchronises."""
+    st = ctypes.c_int(0)
+    _check(lib.b200_sort_status(_ptr(d_temp), _stream(stream), ctypes.byref(st)), "b200_sort_status")
+    return st.value
+
+
+def set_key_range_probe(enable: bool) -> bool:
+    """b200_set_key_range_probe: False = sort calls never wait on the host.  Returns the previous setting."""
+    return bool(lib.b200_set_key_range_probe(int(enable)))
 
 
 def prof_launches() -> int:

@@ -5,6 +5,8 @@
 #include "../../include/b200sort.h"
 #include "common.cuh"
 #include "sort_api.h"
+#include "msb_sched.cuh"
+#include <cstddef>
 
 #include <cstdio>
 #include <cstring>
@@ -17,6 +19,7 @@ using namespace b200;
 // ---- per-kernel timing (sort_api.h: ProfScope) -----------------------------------------------------------------
 namespace b200 {
 int g_prof_enabled = 0;
+int g_key_range_probe = 1;
 unsigned long long g_prof_launches = 0;
 namespace {
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };
@@ -39,6 +42,8 @@ void prof_end(cudaStream_t s) {
   if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, s);
 }
 }  // namespace b200
+
+namespace b200 { size_t status_word_offset() { return offsetof(MsbCounters, error); } }
 
 namespace {
 
@@ -84,7 +89,7 @@ struct HostPathCache {
     return e;
   }
 };
-HostPathCache g_cache;
+HostPathCache g_caches[64];          // one per device: a process may drive several GPUs
 
 int sort_host(bool msb, const void* hk, const void* hv, uint64_t n, void* hko, void* hvo, int key_type, int value_bytes, int descending) {
   Twiddle tw; int kb;
@@ -92,6 +97,9 @@ int sort_host(bool msb, const void* hk, const void* hv, uint64_t n, void* hko, v
   if (value_bytes != 0 && value_bytes != 4 && value_bytes != 8) return (int)cudaErrorInvalidValue;
   if ((value_bytes != 0) != (hv != nullptr)) return (int)cudaErrorInvalidValue;
   if (n == 0) return 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  HostPathCache& g_cache = g_caches[(dev >= 0 && dev < 64) ? dev : 0];
   std::lock_guard<std::mutex> lock(g_cache.mu);
   cudaError_t e;
   if (!g_cache.stream && (e = cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
@@ -219,6 +227,32 @@ int b200_msb_sort(void* d_keys, void* d_values, uint64_t num_items, void* d_keys
                   void** out_values) {
   return b200_msb_sort_bits(d_keys, d_values, num_items, d_keys_alt, d_values_alt, key_type, value_bytes, 0, 64, d_workspace, workspace_bytes, stream,
                             out_keys, out_values);
+}
+
+int b200_host_cache_release(void) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  HostPathCache& c = g_caches[(dev >= 0 && dev < 64) ? dev : 0];
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (int i = 0; i < 5; ++i) { if (c.buf[i]) cudaFree(c.buf[i]); c.buf[i] = nullptr; c.cap[i] = 0; }
+  return 0;
+}
+
+int b200_set_key_range_probe(int enable) {
+  const int old = b200::g_key_range_probe;
+  b200::g_key_range_probe = enable ? 1 : 0;
+  return old;
+}
+
+int b200_sort_status(const void* d_temp, b200_stream_t stream, int* status) {
+  if (d_temp == nullptr || status == nullptr) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint32_t err = 0;
+  cudaError_t e = cudaMemcpyAsync(&err, reinterpret_cast<const char*>(d_temp) + b200::status_word_offset(), sizeof err, cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return (int)e;
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return (int)e;
+  *status = (int)err;
+  return 0;
 }
 
 int b200_msb_sort_host(const void* h_keys, const void* h_values, uint64_t num_items, void* h_sorted_keys, void* h_sorted_values,

@@ -11,6 +11,8 @@ struct Twiddle;
 // Optional per-kernel timing (b200_prof_enable / b200_prof_report in the C ABI): when enabled, every launch site is
 // bracketed by two CUDA events on the launching stream.  Off by default -- a disabled scope costs one load and a branch.
 extern int g_prof_enabled;
+extern int g_key_range_probe;      // b200_set_key_range_probe: 0 = never wait on the host inside a sort call
+size_t status_word_offset();      // where MsbCounters::error lives inside the temporary storage of the MSD engine
 extern unsigned long long g_prof_launches;      // kernels launched while profiling is enabled (b200_prof_launches)
 inline void note_launch() { if (g_prof_enabled) ++g_prof_launches; }
 void prof_begin(const char* name, cudaStream_t s);

@@ -23,10 +23,15 @@ namespace b200 {
 
 #define B200_CHECK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)
 
+// Everything cached per process is cached PER DEVICE (a process may drive several GPUs, like callers of the CUB and reference
+// entry points can): SM counts, the persistent-grid sizes (and the cudaFuncSetAttribute call that goes with them), probe events.
+constexpr int MAX_DEVICES = 64;
+inline int current_device() { int dev = 0; cudaGetDevice(&dev); return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0; }
 inline int num_sms() {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  return sms;
+  static int sms[MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
 }
 
 // One launch of the sort's kernel chain: ordinary, or (B200_PDL) with programmatic stream serialisation.
@@ -105,7 +110,8 @@ inline cudaError_t launch_scatter_fast(const ScatterArgs& a, uint32_t tiles_hint
   using C = Cfg<K, VB>;
   auto kernel = scatter_fast_kernel<K, VB, C::THREADS, C::IPT, C::OCC>;
   constexpr size_t smem = sizeof(FastSmem<K, VB, C::THREADS, C::IPT>);
-  static int grid = 0;
+  static int grids[MAX_DEVICES] = {};
+  int& grid = grids[current_device()];
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
   ProfScope prof("scatter", s);
@@ -119,7 +125,8 @@ inline cudaError_t launch_scatter_stable_fast(const ScatterArgs& a, uint32_t til
   auto kernel = scatter_stable_fast_kernel<K, VB, C::THREADS, C::IPT, C::OCC>;
   constexpr size_t smem = sizeof(StableFastSmem<K, VB, C::THREADS, C::IPT>);
   static_assert(smem <= 113 * 1024, "two stable scatter CTAs must fit one SM");
-  static int grid = 0;
+  static int grids[MAX_DEVICES] = {};
+  int& grid = grids[current_device()];
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
   ProfScope prof("scatter_stable", s);
@@ -133,7 +140,8 @@ inline cudaError_t launch_scatter_exchange(const ScatterArgs& a, uint32_t tiles_
   auto kernel = scatter_stable_fast_kernel<K, VB, C::THREADS, C::IPT, C::OCC, true>;
   constexpr size_t smem = sizeof(StableFastSmem<K, VB, C::THREADS, C::IPT, true>);
   static_assert(smem <= 113 * 1024, "two exchange scatter CTAs must fit one SM");
-  static int grid = 0;
+  static int grids[MAX_DEVICES] = {};
+  int& grid = grids[current_device()];
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
   ProfScope prof("exchange_scatter", s);
@@ -149,7 +157,8 @@ inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cud
   auto kernel = scatter_kernel<K, VB, C::THREADS, C::IPT, C::OCC, MODE, ORD>;
   constexpr size_t smem = sizeof(ScatterSmem<K, VB, C::THREADS, C::IPT, MODE, ORD>);
   static_assert(smem <= (C::OCC >= 2 ? 113 : 227) * 1024, "the scatter CTAs of one SM must fit its 228 KB of shared memory");
-  static int grid = 0;
+  static int grids[MAX_DEVICES] = {};
+  int& grid = grids[current_device()];
   if (!grid) B200_CHECK(persistent_grid(kernel, C::THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(tiles_hint, 1u));
   ProfScope prof(MODE == MODE_RANGE ? "range_partition" : (MODE == MODE_LSB ? "scatter_onesweep" : (ORD ? "scatter_stable" : "scatter")), s);
@@ -165,7 +174,8 @@ inline cudaError_t launch_local(const LocalArgs& a, uint32_t items_hint, cudaStr
   auto kernel = local_sort_kernel<K, VB, THREADS, IPT, ALGO, STABLE>;
   constexpr size_t smem = sizeof(LocalSmem<K, VB, THREADS, IPT, ALGO>);
   static_assert(smem <= 227 * 1024, "local sort exceeds the 227 KB shared-memory limit");
-  static int grid = 0;
+  static int grids[MAX_DEVICES] = {};
+  int& grid = grids[current_device()];
   if (!grid) B200_CHECK(persistent_grid(kernel, THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
   ProfScope prof(ALGO == ALGO_LSD ? (SMALL ? "local_sort_lsd_small" : "local_sort_lsd") : "local_sort_count", s);
@@ -185,7 +195,8 @@ inline cudaError_t launch_bitmap(const LocalArgs& a, uint32_t items_hint, cudaSt
   using C = Cfg<K, VB>;
   auto kernel = bitmap_sort_kernel<K, B200_BITMAP_THREADS, C::LOCAL_CAP, B200_BITMAP_OCC>;
   constexpr size_t smem = sizeof(BitmapSmem<K, B200_BITMAP_THREADS, C::LOCAL_CAP>);
-  static int grid = 0;
+  static int grids[MAX_DEVICES] = {};
+  int& grid = grids[current_device()];
   if (!grid) B200_CHECK(persistent_grid(kernel, B200_BITMAP_THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
   ProfScope prof("local_sort_bitmap", s);
@@ -215,7 +226,8 @@ inline cudaError_t launch_rank(const LocalArgs& a, uint32_t items_hint, cudaStre
   constexpr int OCC_SET = VB ? B200_RANK_OCC : B200_RANK_OCC0;
   constexpr int OCC = OCC_SET ? OCC_SET : (int)std::min<size_t>((227 * 1024) / (smem + 1024), 2048 / THREADS);
   auto kernel = rank_sort_kernel<K, VB, THREADS, IPT, OCC, STABLE>;
-  static int grid = 0;
+  static int grids[MAX_DEVICES] = {};
+  int& grid = grids[current_device()];
   if (!grid) B200_CHECK(persistent_grid(kernel, THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
   ProfScope prof("local_sort_rank", s);
@@ -303,7 +315,8 @@ inline unsigned long long* probe_buffer() {
   return p;
 }
 inline cudaEvent_t probe_event() {
-  static thread_local cudaEvent_t ev = nullptr;
+  static thread_local cudaEvent_t evs[MAX_DEVICES] = {};
+  cudaEvent_t& ev = evs[current_device()];
   if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
   return ev;
 }
@@ -394,6 +407,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   // while the stream is being captured into a CUDA graph.
   // probe = 1: OR / AND of the leading digit from the level-0 histogram (free); 2: exact per-key OR / AND; 0: none
   int probe = (n >= PROBE_MIN_ITEMS && levels > 1 && segin == nullptr) ? 1 : 0;
+  if (!g_key_range_probe) probe = 0;                                                          // b200_set_key_range_probe(0): strictly host-asynchronous calls
   { static const char* e = getenv("B200SORT_PROBE"); if (e && e[0] == '0') probe = 0; }      // measurement switch
   if (probe) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -583,6 +597,7 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     tick_status = cv.take<uint32_t>(64 + max_tiles * RADIX);     // [ticket | pad | status...], one memset clears both
     w.ctr = cv.take<MsbCounters>(1);
     w.locals[0] = cv.take<LocalItem>(1);
+    w.max_locals = 1;                      // (inputs that fit one CTA take the single-item on-chip sort)
   } else {
     msd_carve<K, VB>(cv, n, w);
   }
@@ -606,9 +621,11 @@ cudaError_t lsb_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void* k1, 
     // two buffers: the last possible level lands in buffer (passes & 1), so that is where everything is finished
     // (DoubleBuffer semantics: the selector says where); pointer overloads always deliver into the alternate buffers
     int fin = 1;
-    // keys-only: equal keys are indistinguishable, so the cheaper unstable engine returns the identical result
-    const cudaError_t e = VB == 0 ? msd_sort_run<K, VB, false>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s)
-                                  : msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s);
+    // keys-only over the WHOLE key: equal keys are indistinguishable, so the cheaper unstable engine returns the identical result.
+    // On a bit sub-range keys that tie on the window still differ elsewhere and must keep their input order (cub::DeviceRadixSort::SortKeys).
+    const bool any_order = VB == 0 && begin_bit == 0 && end_bit == KEY_BITS;
+    const cudaError_t e = any_order ? msd_sort_run<K, VB, false>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s)
+                                    : msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s);
     if (selector) *selector = fin;
     return e;
   }
@@ -697,8 +714,9 @@ cudaError_t segmented_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void
   }
   void* bufk[3] = {k0, k1, k2}; void* bufv[3] = {v0, v1, v2};
   int fin = 1;
-  const cudaError_t e = VB == 0 ? msd_sort_run<K, VB, false>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si)
-                                : msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si);
+  const bool any_order = VB == 0 && begin_bit == 0 && end_bit == KEY_BITS;       // (see lsb_sort_impl)
+  const cudaError_t e = any_order ? msd_sort_run<K, VB, false>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si)
+                                  : msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si);
   if (selector) *selector = fin;
   return e;
 }

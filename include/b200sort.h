@@ -3,7 +3,8 @@
  *
  * This is the drop-in boundary for the reference's two host entry-point families (anilshanbhag/gpu-sort); each
  * entry point cites the reference interface it replaces (paths relative to the reference tree).  The reference has
- * no FFI layer -- its boundary is C++ templates -- so include/b200sort_shims.cuh re-creates those template names on
+ * no FFI layer -- its boundary is C++ templates -- so include/b200sort_cub_shim.cuh (cub::DeviceRadixSort /
+ * DeviceSegmentedRadixSort) and include/shim/sort/gpu_radix_sort.h (rdxsrt_unstable_sort) re-create those template names on
  * top of this ABI, and INTEGRATION.md shows how lsb/sort.cu, msb/src/test.cu and msb/tests are re-pointed at them.
  *
  * Conventions
@@ -14,7 +15,9 @@
  *     times per pass and cudaMallocs inside the call, gpu_radix_sort.h:224-228,387,489-491).  One exception, for
  *     num_items >= 2^22 outside CUDA-graph capture: after enqueuing the whole sort the call waits for a 24-byte
  *     read-back taken behind the first histogram (key-range probe), i.e. it returns while the
- *     device is still sorting but not before the first pass over the keys has finished;
+ *     device is still sorting but not before the first pass over the keys has finished.  A caller that needs strictly
+ *     host-asynchronous calls (e.g. the stream waits on work this host thread has not submitted yet) turns the probe off with
+ *     b200_set_key_range_probe(0); sorts then never wait, at the price of whole sweeps on leading digits all keys share;
  *   - item counts are 64-bit (reference: int / unsigned int, device_radix_sort.cuh:154, gpu_radix_sort.h:190);
  *   - key order is the reference's bit-transform order (cub::Traits<T>::TwiddleIn, lsb/cub/cub/util_type.cuh:966-1089):
  *     unsigned as is, signed with the sign bit flipped, floating point as -NaN < -inf < ... < -0.0 < +0.0 < ... < +inf < +NaN.
@@ -131,7 +134,8 @@ B200_API int b200_msb_sort_bits(void* d_keys, void* d_values, uint64_t num_items
                        void** out_keys, void** out_values);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Host-pointer convenience wrappers (allocate device buffers, H2D, sort, D2H, free; synchronous).
+ * Host-pointer convenience wrappers (device buffers, H2D, sort, D2H; synchronous).  The device buffers are kept cached per device
+ * between calls (grow-only: the reference pays cudaMalloc/cudaFree on every call); b200_host_cache_release() frees them.
  * Replace rdxsrt_unstable_sort_keys / rdxsrt_unstable_sort_pairs  msb/src/sort/gpu_radix_sort.h:510-541, 543-587
  * and give the LSB path the same shape.  h_* may be pageable or pinned host memory; outputs may alias inputs.
  * ------------------------------------------------------------------------------------------------------------------ */
@@ -140,12 +144,26 @@ B200_API int b200_msb_sort_host(const void* h_keys, const void* h_values, uint64
 B200_API int b200_lsb_sort_host(const void* h_keys, const void* h_values, uint64_t num_items,
                        void* h_sorted_keys, void* h_sorted_values, int key_type, int value_bytes, int descending);
 
+/* Process-wide switch of the key-range probe (see "Conventions" above): 0 = no sort call ever waits on the host; returns the
+ * previous setting.  Default 1. */
+B200_API int b200_set_key_range_probe(int enable);
+
+/* Device-side status of the last sort that used d_temp (b200_lsb_sort / b200_segmented_sort temporary storage or a
+ * b200_msb_sort workspace): 0 = ok; bit 0 = segment list overflow or a segment offset outside [0, num_items] (the segment was
+ * dropped), bit 1 = an on-chip work list overflowed, bit 2 = tile list overflow.  A non-zero status means the output is not
+ * completely sorted (the reference exits the process in the corresponding situations, msb/src/sort/gpu_radix_sort.h:397-400).
+ * Copies one word back and synchronises `stream`. */
+B200_API int b200_sort_status(const void* d_temp, b200_stream_t stream, int* status);
+
+/* Frees the device buffers the host-pointer wrappers keep cached on the current device between calls. */
+B200_API int b200_host_cache_release(void);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Multi-GPU building blocks (one process per GPU; the collectives themselves are issued by the caller, see
  * gpu_sort_b200/dist.py).  No reference counterpart: the reference is single-GPU.
  *
- *   b200_msd_histogram  : counts[b] = number of keys whose top `bits` (<= 16) bits of the order-transformed key
- *                         equal b (bits <= 14); counts is uint64[1 << bits] on the device and is overwritten.
+ *   b200_msd_histogram  : counts[b] = number of keys whose top `bits` (1 <= bits <= 14) bits of the order-transformed key
+ *                         equal b; counts is uint64[1 << bits] on the device and is overwritten.
  *   b200_range_partition: stable G-way partition of (keys, values) by destination rank, where the destination of a
  *                         key is the index of the first splitter strictly greater than its transformed top-`bits`
  *                         bucket: dest = #{ j : d_splitters[j] <= bucket }, splitters ascending, num_parts-1 of them.

@@ -588,7 +588,8 @@ def test_device_generator_equals_oracle_generator(gs, oracle, dist, param, bits)
 @pytest.mark.parametrize("kt,vb", [("u32", 0), ("u32", 4), ("u64", 8), ("f32", 4), ("i64", 0)])
 def test_device_checker_equals_oracle_and_flags_corruption(gs, oracle, kt, vb):
     n = 200003
-    k = raw_keys(oracle, n, kt, seed=5, dist="entropy", param=2)          # plenty of duplicates
+    k = raw_keys(oracle, n, kt, seed=5, dist="entropy", param=2)
+    k[n // 2:n // 2 + n // 4] = k[:n // 4]                                  # plenty of duplicates, whatever the key width
     v = iota(n, vb)
     ek, ev = oracle.lsb_sort(k, v, key_type=kt)
     dk, dv = dev(ek), dev(ev)
@@ -606,7 +607,8 @@ def test_device_checker_equals_oracle_and_flags_corruption(gs, oracle, kt, vb):
     assert bad2 > 0 and bad2 == oracle.count_unsorted(sw, kt)
     assert (s2, x2) == (s, x)                                              # (a swap keeps the multiset: only the order check can see it)
     # one key overwritten: sortedness may survive, the multiset digest must not
-    ck = ek.copy(); ck[n // 2] = ck[n // 2 - 1]
+    q = int(np.nonzero(ek[1:] != ek[:-1])[0][0]) + 1                       # first position whose key differs from its predecessor
+    ck = ek.copy(); ck[q] = ck[q - 1]
     s3, x3, _, _ = gs.check(dev(ck), dv, key_type=KT_ID[kt])
     assert (s3, x3) != (s, x) and (s3, x3) == oracle.digest(ck, ev)
     if vb:
@@ -722,3 +724,74 @@ def test_reference_msb_driver_runs_on_this_library(gs):
     p, env, root = _ref_binary("msb_test_on_b200sort")
     r = subprocess.run([p], env=env, cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Keys-only sorts on a bit sub-range are STABLE (keys that tie on the window differ elsewhere and keep their input order,
+# cub::DeviceRadixSort::SortKeys); device-side errors are reported; the host-wait switch.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [(0, 8), (4, 20), (15, 17), (8, 32), (0, 16), (1, 31)])
+@pytest.mark.parametrize("n", [5000, 250000, (1 << 21) + 11])
+def test_lsb_keys_only_bit_subranges_are_stable(gs, oracle, bits, n):
+    k = raw_keys(oracle, n, "u32", seed=4)
+    rk, _ = run_lsb(gs, k, None, "u32", begin_bit=bits[0], end_bit=bits[1])
+    ek, _ = oracle.lsb_sort(k, None, key_type="u32", begin_bit=bits[0], end_bit=bits[1])
+    assert same_bits(rk, ek)
+
+
+def test_segmented_keys_only_bit_subrange_is_stable(gs, oracle):
+    n = 400000
+    k = raw_keys(oracle, n, "u64", seed=6)
+    cuts = np.sort(np.random.default_rng(1).integers(0, n, size=40))
+    begin = np.concatenate([[0], cuts]).astype(np.int64); end = np.concatenate([cuts, [n]]).astype(np.int64)
+    k0 = dev(k); k1 = torch.empty_like(k0)
+    dk = gs.DoubleBuffer(k0, k1)
+    b, e = torch.from_numpy(begin).cuda(), torch.from_numpy(end).cuda()
+    tb = gs.DeviceSegmentedRadixSort.SortKeys(None, dk, n, begin.size, b, e, begin_bit=20, end_bit=44, key_type=KT_ID["u64"])
+    temp = torch.empty(tb, dtype=torch.uint8, device="cuda")
+    gs.DeviceSegmentedRadixSort.SortKeys(temp, dk, n, begin.size, b, e, begin_bit=20, end_bit=44, key_type=KT_ID["u64"])
+    torch.cuda.synchronize()
+    ek, _ = oracle.segmented_sort(k, None, begin, end, key_type="u64", begin_bit=20, end_bit=44)
+    assert same_bits(host(dk.Current(), k.dtype), ek)
+    assert gs.sort_status(temp) == 0
+
+
+def test_device_side_errors_are_reported(gs, oracle):
+    """Segment offsets outside [0, n]: the segment is dropped and b200_sort_status says so (the call itself returns cudaSuccess:
+    the offsets live on the device)."""
+    n = 100000
+    k = raw_keys(oracle, n, "u32", seed=2)
+    begin = torch.tensor([0, 50000, 90000], dtype=torch.int64, device="cuda")
+    end = torch.tensor([50000, 90000, n + 5], dtype=torch.int64, device="cuda")          # the last segment runs past the end
+    k0 = dev(k); k1 = torch.empty_like(k0)
+    dk = gs.DoubleBuffer(k0, k1)
+    tb = gs.DeviceSegmentedRadixSort.SortKeys(None, dk, n, 3, begin, end, key_type=KT_ID["u32"])
+    temp = torch.empty(tb, dtype=torch.uint8, device="cuda")
+    gs.DeviceSegmentedRadixSort.SortKeys(temp, dk, n, 3, begin, end, key_type=KT_ID["u32"])
+    assert gs.sort_status(temp) & 1
+    got = host(dk.Current(), k.dtype)
+    assert np.array_equal(got[:50000], np.sort(k[:50000])) and np.array_equal(got[50000:90000], np.sort(k[50000:90000]))      # the valid segments are sorted
+    end[2] = n
+    dk = gs.DoubleBuffer(dev(k), k1)
+    gs.DeviceSegmentedRadixSort.SortKeys(temp, dk, n, 3, begin, end, key_type=KT_ID["u32"])
+    assert gs.sort_status(temp) == 0
+
+
+def test_key_range_probe_switch(gs, oracle):
+    """b200_set_key_range_probe(0): the call never waits on the host; results are identical (small-range keys just take more sweeps)."""
+    n = (1 << 22) + 77
+    k = (raw_keys(oracle, n, "u64", seed=9) & np.uint64(0xFFFFF)).astype(np.uint64)       # keys < 2^20 in 64-bit words
+    exp = np.sort(k)
+    def msb():
+        k0 = dev(k); k1 = torch.empty_like(k0)
+        r = gs.rdxsrt_unstable_sort(k0, None, n, k1, None, key_type=KT_ID["u64"])
+        torch.cuda.synchronize()
+        return host(r.sorted_keys, k.dtype), r.sorted_keys.data_ptr() == k0.data_ptr()
+    old = gs.set_key_range_probe(False)
+    try:
+        got, in_input = msb()
+        assert same_bits(got, exp) and in_input          # no probe: all 8 levels are planned, the result lands in the input buffer like the reference's
+        assert same_bits(run_lsb(gs, k, None, "u64")[0], exp)
+    finally:
+        gs.set_key_range_probe(old)
+    assert same_bits(msb()[0], exp)
