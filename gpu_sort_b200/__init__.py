@@ -220,7 +220,7 @@ class DeviceSegmentedRadixSort:
 
     @staticmethod
     def _run(d_temp_storage, d_keys, d_values, num_items, num_segments, d_begin_offsets, d_end_offsets, begin_bit, end_bit,
-             descending, stream, key_type, keys_out=None, values_out=None):
+             descending, stream, key_type, keys_out=None, values_out=None, ties_are_equal=False):
         overwrite = keys_out is None
         if overwrite:
             k_cur, k_alt = d_keys.Current(), d_keys.Alternate()
@@ -238,7 +238,7 @@ class DeviceSegmentedRadixSort:
         sel = ctypes.c_int(0)
         err = lib.b200_segmented_sort(_ptr(d_temp_storage), ctypes.byref(nbytes), _ptr(k_cur), _ptr(k_alt), _ptr(v_cur), _ptr(v_alt),
                                       ctypes.byref(sel), num_items, num_segments, _ptr(d_begin_offsets), _ptr(d_end_offsets), ob,
-                                      kt, vb, begin_bit, end_bit, int(descending), int(overwrite), _stream(stream))
+                                      kt, vb, begin_bit, end_bit, int(descending), int(overwrite) | (2 if ties_are_equal else 0), _stream(stream))
         _check(err, "b200_segmented_sort")
         if d_temp_storage is None:
             return nbytes.value

@@ -23,6 +23,7 @@ namespace b200 {
 
 constexpr int RANK_BITS = 16;
 constexpr int RANK_ENT = (1 << RANK_BITS) / 16;       // 16 cells per entry
+constexpr int RANK_DENSE_BITS = 15;    // DENSE: 2^15 cells x 4-bit counters fill lo[]
 constexpr int RANK_EXTRA = 15;         // (<= 15: the scan counts the listed copies of an entry in a 4-bit field)
 
 template <typename K, int VB, int THREADS, int IPT, bool STABLE>
@@ -49,9 +50,12 @@ struct RankSmem {
 // A copy of a block-uniform value the compiler cannot see through: the row tests of each phase (`j < rows_full`) are then
 // evaluated where they are used (one compare per row) instead of being computed once, packed into a register bit mask and
 // unpacked again in every phase (measured: 6 instructions per key, profiles/r02_rank_v2.txt).
+// sum of the eight 4-bit fields of x
+__device__ __forceinline__ uint32_t nibble_sum(uint32_t x) { return __dp4a(x & 0x0F0F0F0Fu, 0x01010101u, __dp4a((x >> 4) & 0x0F0F0F0Fu, 0x01010101u, 0u)); }
+
 __device__ __forceinline__ uint32_t opaque(uint32_t x) { uint32_t y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; }
 
-template <typename K, int VB, int THREADS, int IPT, int OCC, bool STABLE>
+template <typename K, int VB, int THREADS, int IPT, int OCC, bool STABLE, bool DENSE = false>
 __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_constant__ LocalArgs a) {
   pdl_wait();
   using SM = RankSmem<K, VB, THREADS, IPT, STABLE>;
@@ -69,6 +73,18 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
 
   auto stage_item = [&](int slot, uint32_t i, const LocalItem& it) {
     if (i < num_items) {
+      if (!DENSE && a.dense != nullptr) {
+        // more than one key per twelve cells: third copies of a value are no longer rare (measured: at one per eight most buckets
+        // exceed the short list) -- the 4-bit-counter variant takes the bucket (passed on before anything of it is read)
+        const int nb = (int)it.nbits - a.begin_bit;
+        if (nb <= RANK_DENSE_BITS && (unsigned long long)it.cnt * 12ull > (1ull << (nb > 0 ? nb : 0))) {
+          const uint32_t o = atomicAdd(a.num_dense_ptr, 1u);
+          if (o < a.max_items) a.dense[o] = it; else atomicOr(a.error_ptr, 2u);
+          LocalItem skip = it; skip.cnt = 0xFFFFFFFEu;      // "nothing staged": the block moves on to its next bucket
+          sm.item[slot] = skip;
+          return;
+        }
+      }
       const BulkWindow<K> bw(reinterpret_cast<const K*>(a.keys[it.src]), it.off, it.cnt);
       uint32_t bytes = bw.bytes;
       sm.skew[slot] = bw.skew;
@@ -103,6 +119,7 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
   }
   __syncthreads();
 
+  uint32_t phase = 0u;                       // bit s: mbarrier phase parity of staging slot s (a slot whose bucket was passed on is not armed)
   for (uint32_t iter = 0;; ++iter) {
     const int slot = (int)(iter & 1u);
     const LocalItem it = sm.item[slot];
@@ -118,9 +135,16 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
     K* __restrict__ sk = &sm.stage[slot][0];
     V* __restrict__ sv = &sm.vstage[VB ? slot : 0][0];
     const uint32_t cells = nb > 0 ? 1u << (nb > RANK_BITS ? RANK_BITS : nb) : 1u, cmask = cells - 1u;
-    const uint32_t nent = cells > 16u ? cells >> 4 : 1u;
-    bool sorted = nb <= RANK_BITS && cnt <= 2u * cells + RANK_EXTRA;      // block-uniform
-    mbar_wait(&sm.bar[slot], (iter >> 1) & 1u);
+    // entries of lo[] in use: 16 cells per entry (presence + second-copy bits), DENSE: 8 cells per entry (4-bit counters)
+    const uint32_t nent = DENSE ? (cells > 8u ? cells >> 3 : 1u) : (cells > 16u ? cells >> 4 : 1u);
+    bool sorted = DENSE ? (nb <= RANK_DENSE_BITS && cnt <= 15u * cells) : (nb <= RANK_BITS && cnt <= 2u * cells + RANK_EXTRA);      // block-uniform
+    if (cnt == 0xFFFFFFFEu) {                  // passed on to the dense variant by the producer: nothing was staged
+      __syncthreads();
+      if (tid == PRODUCER) it_a = it_b;
+      continue;
+    }
+    mbar_wait(&sm.bar[slot], (phase >> slot) & 1u);
+    phase ^= 1u << slot;
     // the sorted bucket is built at sk[aoff ..) / sv[voff ..): same 16-byte phase as its place in the output arrays
     const uint32_t aoff = (uint32_t)((reinterpret_cast<uintptr_t>(keys_out + it.off) & 15u) / sizeof(K));
     const uint32_t voff = VB ? (uint32_t)((reinterpret_cast<uintptr_t>(vals_out + it.off) & 15u) / sizeof(V)) : 0u;
@@ -143,13 +167,24 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
         key_last = twiddle_in<K>(key_last, a.tw);
       }
       uint32_t notfirst = 0;
+      unsigned long long arrs = 0;               // DENSE: 4-bit arrival index of each of the first 16 keys of this thread
+      uint32_t arrs_hi = 0, full15 = 0;          //        ... and of keys 16, 17 (and of the incomplete row, at field rows_full)
       const uint32_t lo_base = smem_u32(sm.lo), hi_base = smem_u32(sm.hi);
       const uint32_t outk = smem_u32(sk + aoff), outv = VB ? smem_u32(sv + voff) : 0u, org_base = smem_u32(sm.origin);
       auto mark = [&](K k, uint32_t j) {
         const uint32_t c = (uint32_t)(k >> lo_bit) & cmask;
-        const uint32_t b = c & 15u;
-        const uint32_t old = atoms_or(lo_base + (c >> 4) * 4u, 1u << b);
-        notfirst |= ((old >> b) & 1u) << j;
+        if (!DENSE) {
+          const uint32_t b = c & 15u;
+          const uint32_t old = atoms_or(lo_base + (c >> 4) * 4u, 1u << b);
+          notfirst |= ((old >> b) & 1u) << j;
+        } else {
+          // DENSE: a 4-bit counter per cell; the atomicAdd returns the key's arrival index inside its cell (15 = the cell is full:
+          // the bucket goes to the overflow list -- the add has carried into the neighbouring counter, which no longer matters)
+          const uint32_t sh = (c & 7u) * 4u;
+          const uint32_t a4 = (atoms_add(lo_base + (c >> 3) * 4u, 1u << sh) >> sh) & 15u;
+          full15 |= a4 == 15u ? 1u : 0u;
+          if (j < 16u) arrs |= (unsigned long long)a4 << (4u * j); else arrs_hi |= a4 << (4u * (j - 16u));
+        }
       };
       {
         const uint32_t rf = opaque(rows_full);
@@ -158,19 +193,23 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
           if ((uint32_t)j < rf) mark(key[j], j);
       }
       if (has_last) mark(key_last, rows_full);
-      for (uint32_t m = notfirst; m;) {          // the few keys whose cell was taken: second-copy bit, then the short list
-        const int j = __ffs(m) - 1;
-        m &= m - 1u;
-        const uint32_t idx = (uint32_t)j * THREADS + tid;
-        K k = sk[skew + idx];                    // (the staged keys are intact until the barrier below)
-        if (a.tw_in) k = twiddle_in<K>(k, a.tw);
-        const uint32_t c = (uint32_t)(k >> lo_bit) & cmask;
-        const uint32_t bit = 0x10000u << (c & 15u);
-        const uint32_t old = atomicOr(&sm.lo[c >> 4], bit);
-        if (old & bit) {
-          const uint32_t x = atomicAdd(&sm.nextra, 1u);
-          if (x < (uint32_t)RANK_EXTRA) sm.extras[x] = c | (idx << 16);
+      if (!DENSE) {
+        for (uint32_t m = notfirst; m;) {          // the few keys whose cell was taken: second-copy bit, then the short list
+          const int j = __ffs(m) - 1;
+          m &= m - 1u;
+          const uint32_t idx = (uint32_t)j * THREADS + tid;
+          K k = sk[skew + idx];                    // (the staged keys are intact until the barrier below)
+          if (a.tw_in) k = twiddle_in<K>(k, a.tw);
+          const uint32_t c = (uint32_t)(k >> lo_bit) & cmask;
+          const uint32_t bit = 0x10000u << (c & 15u);
+          const uint32_t old = atomicOr(&sm.lo[c >> 4], bit);
+          if (old & bit) {
+            const uint32_t x = atomicAdd(&sm.nextra, 1u);
+            if (x < (uint32_t)RANK_EXTRA) sm.extras[x] = c | (idx << 16);
+          }
         }
+      } else if (full15) {
+        sm.nextra = RANK_EXTRA + 1u;               // any value above RANK_EXTRA: "not sorted"
       }
       __syncthreads();
       const uint32_t nx = sm.nextra;
@@ -186,7 +225,8 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
             const uint4 q = reinterpret_cast<const uint4*>(sm.lo)[g * THREADS + tid];      // (entries past nent are never set)
-            pc[g][0] = __popc(q.x); pc[g][1] = __popc(q.y); pc[g][2] = __popc(q.z); pc[g][3] = __popc(q.w);
+            if (!DENSE) { pc[g][0] = __popc(q.x); pc[g][1] = __popc(q.y); pc[g][2] = __popc(q.z); pc[g][3] = __popc(q.w); }
+            else { pc[g][0] = nibble_sum(q.x); pc[g][1] = nibble_sum(q.y); pc[g][2] = nibble_sum(q.z); pc[g][3] = nibble_sum(q.w); }
           }
           uint32_t flags = 0;                    // entries of mine that hold third-or-later copies (almost always none)
           {
@@ -194,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
             static_assert((1 << LOG_T) == THREADS, "entry -> (chunk, thread, word) split");
             unsigned long long xcnt = 0;         // listed copies per entry of mine: 4-bit fields, field = chunk * 4 + word
 #pragma unroll 1
-            for (uint32_t i = 0; i < nx; ++i) {
+            for (uint32_t i = 0; i < (DENSE ? 0u : nx); ++i) {
               const uint32_t xe = (sm.extras[i] & 0xFFFFu) >> 4;
               if (((xe >> 2) & (uint32_t)(THREADS - 1)) == tid) xcnt += 1ull << (4u * (((xe >> (2 + LOG_T)) << 2) | (xe & 3u)));
             }
@@ -251,24 +291,33 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
         uint32_t pos[ORDER ? IPT : 1], pos_last = 0;
         auto place = [&](K k, V v, uint32_t j, uint32_t& pj) {
           const uint32_t c = (uint32_t)(k >> lo_bit) & cmask;
-          const uint32_t e = c >> 4, b = c & 15u;
+          const uint32_t e = c >> (DENSE ? 3 : 4);
           const uint32_t l = lds_u32(lo_base + e * 4u), h = lds_u16(hi_base + e * 2u);
-          const uint32_t below = (0x10001u << b) - 0x10001u;        // the cells below b, first and second copies
-          uint32_t rank = (h & 0x7FFFu) + __popc(l & below);
-          uint32_t arr = (notfirst >> j) & 1u;                       // arrival order inside the cell: 0, 1, (2 + k: rare path)
-          uint32_t mult = ORDER ? 1u + ((l >> (16 + b)) & 1u) : 0u;
-          if (h & 0x8000u) {
-            // rare: the key's entry holds third-or-later copies (listed in extras[], arrival order).  Listed copies in lower cells
-            // of the entry add to the rank, listed copies of the key's own cell to its multiplicity; a listed key gets its arrival index
-            const uint32_t me = c | ((j * THREADS + tid) << 16);
-            uint32_t same = 0;
+          uint32_t rank, arr, mult;
+          if (!DENSE) {
+            const uint32_t b = c & 15u;
+            const uint32_t below = (0x10001u << b) - 0x10001u;        // the cells below b, first and second copies
+            rank = (h & 0x7FFFu) + __popc(l & below);
+            arr = (notfirst >> j) & 1u;                               // arrival order inside the cell: 0, 1, (2 + k: rare path)
+            mult = ORDER ? 1u + ((l >> (16 + b)) & 1u) : 0u;
+            if (h & 0x8000u) {
+              // rare: the key's entry holds third-or-later copies (listed in extras[], arrival order).  Listed copies in lower cells
+              // of the entry add to the rank, listed copies of the key's own cell to its multiplicity; a listed key gets its arrival index
+              const uint32_t me = c | ((j * THREADS + tid) << 16);
+              uint32_t same = 0;
 #pragma unroll 1
-            for (uint32_t i = 0; i < nx; ++i) {
-              const uint32_t x = sm.extras[i], xc = x & 0xFFFFu;
-              rank += ((xc ^ c) < 16u && xc < c) ? 1u : 0u;
-              if (xc == c) { if (x == me) arr = 2u + same; ++same; }
+              for (uint32_t i = 0; i < nx; ++i) {
+                const uint32_t x = sm.extras[i], xc = x & 0xFFFFu;
+                rank += ((xc ^ c) < 16u && xc < c) ? 1u : 0u;
+                if (xc == c) { if (x == me) arr = 2u + same; ++same; }
+              }
+              mult += same;
             }
-            mult += same;
+          } else {
+            const uint32_t sh = (c & 7u) * 4u;
+            rank = h + nibble_sum(l & ((1u << sh) - 1u));            // keys in the lower cells of the entry
+            arr = j < 16u ? (uint32_t)(arrs >> (4u * j)) & 15u : (arrs_hi >> (4u * (j - 16u))) & 15u;
+            mult = (l >> sh) & 15u;
           }
           if (!ORDER) {
             const uint32_t q = rank + arr;
@@ -312,8 +361,10 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
       if (tid == 0) sm.nextra = 0;
     }
     if (!sorted && tid == 0) {
-      const uint32_t o = atomicAdd(a.num_overflow_ptr, 1u);
-      if (o < a.max_items) a.overflow[o] = it; else atomicOr(a.error_ptr, 2u);
+      // too many copies of some value for this variant: the dense variant takes the bucket if it can, the LSD kernel otherwise
+      const bool to_dense = !DENSE && a.dense != nullptr && nb <= RANK_DENSE_BITS;
+      const uint32_t o = atomicAdd(to_dense ? a.num_dense_ptr : a.num_overflow_ptr, 1u);
+      if (o < a.max_items) (to_dense ? a.dense : a.overflow)[o] = it; else atomicOr(a.error_ptr, 2u);
     }
 
     // ---- D: shared-memory vector v and output vector v cover the same elements, both 16-byte aligned

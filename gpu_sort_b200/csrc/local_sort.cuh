@@ -32,6 +32,7 @@ struct LocalArgs {
   uint32_t max_items;                    // capacity of every work list (a count above it means the list overflowed: the error flag is up)
   LocalItem* overflow; uint32_t* num_overflow_ptr;     // ALGO_COUNT / bitmap sort: buckets they could not take
   uint32_t* error_ptr;                   // MsbCounters::error
+  LocalItem* dense; uint32_t* num_dense_ptr;           // rank sort: buckets passed on to its dense variant (nullptr: none)
   int tw_in;                             // keys still in caller form (single-tile sorts)
   int tw_out;
   int begin_bit;                         // lowest bit to sort (0 for MSB items)

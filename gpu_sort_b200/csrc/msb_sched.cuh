@@ -23,7 +23,8 @@ struct MsbCounters {            // one small zero-initialised block in the works
   uint32_t num_bitmap;          // work list of the presence-bitmap sort (large keys-only buckets with <= 16 bits left)
   uint32_t num_direct[2];       // segmented sort: caller segments that fit on chip as they are (large / small on-chip configuration)
   unsigned long long key_or, key_and;     // OR / AND of all transformed keys (level-0 histogram): bits where they agree are constant
-  uint32_t probe_single, pad2;            // (read back together with key_or / key_and) the level-0 histogram has one non-empty bucket
+  uint32_t probe_single, num_dense;       // (probe_single is read back together with key_or / key_and) the level-0 histogram has one non-empty bucket;
+                                          // num_dense: work list of the dense rank sort (large buckets whose keys crowd their cells)
 };
 
 static __global__ void msb_init_kernel(Seg* segs, MsbCounters* c, uint64_t n) {

@@ -217,20 +217,20 @@ inline cudaError_t launch_bitmap(const LocalArgs& a, uint32_t items_hint, cudaSt
 #ifndef B200_RANK_OCC0
 #define B200_RANK_OCC0 0
 #endif
-template <typename K, int VB, bool STABLE>
+template <typename K, int VB, bool STABLE, bool DENSE = false>
 inline cudaError_t launch_rank(const LocalArgs& a, uint32_t items_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
-  constexpr int THREADS = VB ? B200_RANK_THREADS : B200_RANK_THREADS0, IPT = C::LOCAL_CAP / THREADS;
+  constexpr int THREADS = (VB || DENSE) ? B200_RANK_THREADS : B200_RANK_THREADS0, IPT = C::LOCAL_CAP / THREADS;
   static_assert(THREADS * IPT == C::LOCAL_CAP, "the rank kernel's capacity is the on-chip capacity of the configuration");
   constexpr size_t smem = sizeof(RankSmem<K, VB, THREADS, IPT, STABLE>);
-  constexpr int OCC_SET = VB ? B200_RANK_OCC : B200_RANK_OCC0;
-  constexpr int OCC = OCC_SET ? OCC_SET : (int)std::min<size_t>((227 * 1024) / (smem + 1024), 2048 / THREADS);
-  auto kernel = rank_sort_kernel<K, VB, THREADS, IPT, OCC, STABLE>;
+  constexpr int OCC_SET = (VB || DENSE) ? B200_RANK_OCC : B200_RANK_OCC0;
+  constexpr int OCC = OCC_SET ? OCC_SET : (int)std::min<size_t>((227 * 1024) / (smem + 1024), THREADS >= 512 ? 2 : 2048 / THREADS);      // (512 threads: 64 registers each)
+  auto kernel = rank_sort_kernel<K, VB, THREADS, IPT, OCC, STABLE, DENSE>;
   static int grids[MAX_DEVICES] = {};
   int& grid = grids[current_device()];
   if (!grid) B200_CHECK(persistent_grid(kernel, THREADS, smem, &grid));
   const int g = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint32_t>(items_hint, 1u));
-  ProfScope prof("local_sort_rank", s);
+  ProfScope prof(DENSE ? "local_sort_rank_dense" : "local_sort_rank", s);
   launch_k(kernel, g, THREADS, smem, s, a);
   return cudaGetLastError();
 }
@@ -276,7 +276,7 @@ struct Carver {      // sub-allocates the caller's temporary storage, 256-byte a
 // ===============================================================================================================
 struct MsdWorkspace {
   MsbCounters* ctr; Seg* segs0; Seg* segs1; uint32_t* tile_base; TileDesc* descs; uint32_t* seg_hist; uint64_t* bins;
-  uint32_t* tile_off; uint16_t* tile_cnt; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[5];   // LSD list, counting list, overflow, small-bucket LSD list, bitmap list
+  uint32_t* tile_off; uint16_t* tile_cnt; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[6];   // LSD list, counting list, overflow, small-bucket LSD list, rank list, dense rank list
   uint32_t max_segs, max_tiles, max_locals, max_groups;
   unsigned long long* seg_or; unsigned long long* seg_and;      // B200_SEG_CONST: per-segment OR / AND of the keys
 };
@@ -301,7 +301,7 @@ inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
   w.group_tail = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
   w.group_flag = cv.take<uint32_t>(w.max_groups);
   w.carry = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
-  for (int i = 0; i < 5; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
+  for (int i = 0; i < 6; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
 #if B200_SEG_CONST
   w.seg_or = cv.take<unsigned long long>(w.max_segs);
   w.seg_and = cv.take<unsigned long long>(w.max_segs);
@@ -523,7 +523,15 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
         B200_CHECK((launch_local<K, VB, ALGO_COUNT, ORDERED>(la, w.max_locals, s)));
       la.items = w.locals[4]; la.num_items_ptr = &ctr->num_bitmap;                            // large buckets with <= 16 bits left
       if constexpr (sizeof(K) == 4) {
-        if (use_rank) B200_CHECK((launch_rank<K, VB, ORDERED>(la, w.max_locals, s)));
+        if (use_rank) {
+          // buckets whose keys crowd their cells (heavy duplicates, or a key space as dense as the input) are passed on, unread, to the
+          // 4-bit-counter variant of the same kernel
+          la.dense = w.locals[5]; la.num_dense_ptr = &ctr->num_dense;
+          B200_CHECK((launch_rank<K, VB, ORDERED>(la, w.max_locals, s)));
+          la.dense = nullptr; la.num_dense_ptr = nullptr;
+          la.items = w.locals[5]; la.num_items_ptr = &ctr->num_dense;
+          B200_CHECK((launch_rank<K, VB, ORDERED, true>(la, w.max_locals, s)));
+        }
       }
       if constexpr (!ORDERED && VB == 0 && sizeof(K) == 4) {
         if (use_bitmap) B200_CHECK((launch_bitmap<K, VB>(la, w.max_locals, s)));
@@ -687,7 +695,8 @@ cudaError_t segmented_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void
   if (end_bit > KEY_BITS) end_bit = KEY_BITS;
   if (n >= (1ull << 32) || (offset_bytes != 4 && offset_bytes != 8)) return cudaErrorInvalidValue;
   const int passes = end_bit > begin_bit ? (end_bit - begin_bit + 7) / 8 : 0;
-  const bool need_third = !allow_overwrite && passes > 1 && n > (uint64_t)C::LOCAL_CAP;
+  const bool overwrite = (allow_overwrite & 1) != 0;
+  const bool need_third = !overwrite && passes > 1 && n > (uint64_t)C::LOCAL_CAP;
 
   Carver cv(d_temp);
   MsdWorkspace w{};
@@ -705,7 +714,7 @@ cudaError_t segmented_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void
   if (n == 0 || num_segments == 0) return cudaSuccess;
   if (d_begin == nullptr || d_end == nullptr) return cudaErrorInvalidValue;
   if (passes == 0) {
-    if (!allow_overwrite) {
+    if (!overwrite) {
       B200_CHECK(cudaMemcpyAsync(k1, k0, n * sizeof(K), cudaMemcpyDeviceToDevice, s));
       if (VB) B200_CHECK(cudaMemcpyAsync(v1, v0, n * sizeof(V), cudaMemcpyDeviceToDevice, s));
       if (selector) *selector = 1;
@@ -714,9 +723,11 @@ cudaError_t segmented_sort_impl(void* d_temp, size_t* temp_bytes, void* k0, void
   }
   void* bufk[3] = {k0, k1, k2}; void* bufv[3] = {v0, v1, v2};
   int fin = 1;
-  const bool any_order = VB == 0 && begin_bit == 0 && end_bit == KEY_BITS;       // (see lsb_sort_impl)
-  const cudaError_t e = any_order ? msd_sort_run<K, VB, false>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si)
-                                  : msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, allow_overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si);
+  // (see lsb_sort_impl; allow_overwrite bit 1: the caller vouches that keys which tie on the window are equal -- e.g. every segment
+  // shares its bits above end_bit, like the buckets the multi-GPU exchange delivers)
+  const bool any_order = VB == 0 && ((begin_bit == 0 && end_bit == KEY_BITS) || (allow_overwrite & 2));
+  const cudaError_t e = any_order ? msd_sort_run<K, VB, false>(w, bufk, bufv, need_third ? 3 : 2, overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si)
+                                  : msd_sort_run<K, VB, true>(w, bufk, bufv, need_third ? 3 : 2, overwrite ? -1 : 1, &fin, n, tw, begin_bit, end_bit, s, &si);
   if (selector) *selector = fin;
   return e;
 }

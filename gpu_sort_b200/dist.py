@@ -533,7 +533,8 @@ class ExchangeSorter:
         mark("barrier1")
         dk = gs.DoubleBuffer(self.recv_k, self.alt_k)
         dv = gs.DoubleBuffer(self.recv_v, self.alt_v) if self.pairs else None
-        gs.DeviceSegmentedRadixSort._run(self.s_temp, dk, dv, self.cap, 256, self.seg_begin, self.seg_end, 0, self.shift, False, None, self.kt)
+        gs.DeviceSegmentedRadixSort._run(self.s_temp, dk, dv, self.cap, 256, self.seg_begin, self.seg_end, 0, self.shift, False, None, self.kt,
+                                         ties_are_equal=True)          # every bucket shares its leading xbits bits
         mark("finish")
         self._last = (dk.Current(), dv.Current() if self.pairs else None, keys, vals)
         if profile:

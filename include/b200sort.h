@@ -90,7 +90,9 @@ B200_API int b200_lsb_sort(void* d_temp, size_t* temp_bytes,
  *   everything else            : as b200_lsb_sort (two-phase temporary storage, selector_out, [begin_bit,end_bit), descending,
  *                                allow_overwrite).  num_items = length of the key array (< 2^32).
  * Stable inside every segment.
- * ------------------------------------------------------------------------------------------------------------------ */
+ * ------------------------------------------------------------------------------------------------------------------  * allow_overwrite bit 1 (value 2, keys-only): the caller vouches that keys which tie on [begin_bit, end_bit) are EQUAL keys (every
+ * segment shares its remaining bits), so their order is free and the cheaper unstable engine may run.
+ */
 B200_API int b200_segmented_sort(void* d_temp, size_t* temp_bytes,
                         void* d_keys_current, void* d_keys_alternate,
                         void* d_values_current, void* d_values_alternate,
