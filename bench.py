@@ -252,6 +252,22 @@ def run_ours_single(args, wl):
     return line
 
 
+def extra_workloads(args):
+    """BASELINE's metric reads "keys/pairs": the default line also carries the pairs config (cfg3) and the skewed 64-bit config
+    (cfg4, Zipf-hashed keys) as short runs with their own roofline figures (full lines: bench.py --workload cfg3 | cfg4)."""
+    out = {}
+    for name in ("cfg3", "cfg4"):
+        sub = argparse.Namespace(**vars(args))
+        sub.workload = name; sub.steps = max(3, min(args.steps, 5)); sub.warmup = 3; sub.no_cpu = True; sub.no_e2e = True; sub.logn = 0
+        try:
+            l = run_ours_single(sub, WORKLOADS[name])
+            out[name] = {k: l[k] for k in ("value", "unit", "ms_per_step", "ms_median", "value_median", "steps", "dtype", "config", "roofline", "gpu_launches_per_step", "verified")}
+        except Exception as e:          # the headline line must not die with an extra
+            out[name] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours_multi(args, rank, world):
     """BASELINE config 5, weak-scaled: every rank holds 2^logn (default 2^29) uint32 key + uint32 value pairs of ONE global array
     (N = 8 -> 2^32 pairs), sorted with the multi-GPU path of gpu_sort_b200/dist.py (ExchangeSorter: per-tile digit counts,
@@ -524,6 +540,7 @@ def main():
     ap.add_argument("--logn", type=int, default=0, help="override log2(keys per GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="single GPU: skip the short cfg3 / cfg4 runs carried in the default line")
     ap.add_argument("--no-local-ref", action="store_true", help="multi-GPU: skip the single-GPU reference point of the same per-GPU workload")
     ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: NCCL all_to_all_single instead of the fused peer-memory scatter")
     args = ap.parse_args()
@@ -552,6 +569,8 @@ def main():
         dist.destroy_process_group()
     else:
         line = run_ours_single(args, WORKLOADS[args.workload])
+        if args.workload == "cfg2" and not args.logn and not args.no_extras:
+            line["other_configs"] = extra_workloads(args)
     if rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
     return 0

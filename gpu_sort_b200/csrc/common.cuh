@@ -21,11 +21,12 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
-// EXPERIMENTAL, off by default, NOT yet run on a GPU (written after round 1's GPU budget was spent):
-// B200_SEG_CONST=1 lets the MSD levels recognise a segment whose keys are all equal on the bits still to be sorted and
-// finish it by plain copies instead of scattering it at every remaining level (hot keys of duplicate-heavy inputs).
+// B200_SEG_CONST=1 (default): the MSD levels recognise a segment whose keys are all equal on the bits still to be sorted and
+// finish it by plain copies instead of scattering it at every remaining level (hot keys of duplicate-heavy inputs; cf. CUB's
+// short_circuit, lsb/cub/cub/agent/agent_radix_sort_downsweep.cuh:701-724, and the reference's hot-bucket path,
+// msb/src/sort/cuda_radix_sort.h:438-447).  Measured on 2^29 Zipf-hashed u64 keys: 29.3 -> 23.7 ms (profiles/r02_cfg4.txt).
 #ifndef B200_SEG_CONST
-#define B200_SEG_CONST 0
+#define B200_SEG_CONST 1
 #endif
 
 constexpr int RADIX_BITS = 8;
@@ -136,14 +137,15 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* sc
 // ---------------------------------------------------------------------------------------------------------
 struct Seg {            // a bucket that still needs a counting pass ("non-local bucket" in the reference)
   uint64_t off;         // first key index
-  uint64_t cnt;         // number of keys
+  uint32_t cnt;         // number of keys (the MSD engine serves n < 2^32)
+  uint32_t flags;       // bit 0: suspected of holding ONE repeated key (all of its parent's keys fell into this one bucket)
 };
 struct TileDesc {       // one histogram / scatter tile of a segment, self-contained so a tile costs one load
   uint64_t off;         // first key index of the tile
   uint32_t cnt;         // keys in the tile
   uint32_t seg;         // index into the level's Seg list
   uint32_t tile_in_seg;
-  uint32_t pad;
+  uint32_t pad;         // the segment's flags (Seg::flags)
 };
 struct LocalItem {      // a bucket (or merged run of tiny buckets) that is finished on-chip
   uint64_t off;         // first key index

@@ -106,7 +106,7 @@ struct TileHistArgs {
 };
 
 template <typename K, bool RANGE, bool PROBE, bool SEGP = false>
-__global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_constant__ TileHistArgs a) {
+__global__ void __launch_bounds__(HIST_THREADS, sizeof(K) == 4 ? 4 : 2) tile_hist_kernel(const __grid_constant__ TileHistArgs a) {
   pdl_wait();
   __shared__ uint32_t sh[RADIX];
   __shared__ uint32_t s_sor[2], s_sand[2];     // SEGP: OR / AND of the current tile's keys (low, high word)
@@ -122,10 +122,12 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
   if (RANGE) { range_lut_build(rl, a.splitters, a.num_parts, (int)sizeof(K) * 8 - shift); __syncthreads(); }
   const int cshift = RANGE ? rl.cshift : 0;
   K acc_or = (K)0, acc_and = (K)~(K)0;
-  auto count = [&](K k) {
+  // SUS (compile time): the tile belongs to a segment suspected of holding one repeated key (its parent's histogram had a single
+  // non-empty bin): only then is the per-key OR / AND kept -- segments of ordinary inputs pay nothing for the check
+  auto count = [&](K k, auto SUS) {
     if (a.tw_in) k = (K)(k ^ (((K)((S)k >> (sizeof(K) * 8 - 1)) & fl) | sg) ^ fp);
     if (PROBE) { acc_or |= k; acc_and &= k; }
-    if (SEGP) { t_or |= k; t_and &= k; }
+    if (SEGP && decltype(SUS)::value) { t_or |= k; t_and &= k; }
     uint32_t d;
     if (!RANGE) d = digit_of<K>(k, shift, mask);
     else d = range_part(rl, (uint32_t)(k >> shift), cshift);
@@ -157,26 +159,30 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
       const uint32_t head = min(cnt, mis ? VEC - mis : 0u);
       const uint32_t nvec = (cnt - head) / VEC;
       const uint4* pv = reinterpret_cast<const uint4*>(p + head);
-      // batches of four independent 16-byte loads per thread before any counting (memory-level parallelism)
-      for (uint32_t i0 = 0; i0 < nvec; i0 += 4 * HIST_THREADS) {
-        uint4 q[4];
+      const bool sus = SEGP && td.pad != 0;
+      auto count_tile = [&](auto SUS) {
+        // batches of four independent 16-byte loads per thread before any counting (memory-level parallelism)
+        for (uint32_t i0 = 0; i0 < nvec; i0 += 4 * HIST_THREADS) {
+          uint4 q[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t i = i0 + u * HIST_THREADS + tid;
-          q[u] = i < nvec ? pv[i] : make_uint4(0, 0, 0, 0);
-        }
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * HIST_THREADS + tid;
+            q[u] = i < nvec ? pv[i] : make_uint4(0, 0, 0, 0);
+          }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (i0 + u * HIST_THREADS + tid < nvec) {
-            if (sizeof(K) == 4) { count((K)q[u].x); count((K)q[u].y); count((K)q[u].z); count((K)q[u].w); }
-            else { count((K)(((uint64_t)q[u].y << 32) | q[u].x)); count((K)(((uint64_t)q[u].w << 32) | q[u].z)); }
+          for (int u = 0; u < 4; ++u) {
+            if (i0 + u * HIST_THREADS + tid < nvec) {
+              if (sizeof(K) == 4) { count((K)q[u].x, SUS); count((K)q[u].y, SUS); count((K)q[u].z, SUS); count((K)q[u].w, SUS); }
+              else { count((K)(((uint64_t)q[u].y << 32) | q[u].x), SUS); count((K)(((uint64_t)q[u].w << 32) | q[u].z), SUS); }
+            }
           }
         }
-      }
-      if (tid < head) count(p[tid]);
-      const uint32_t tail0 = head + nvec * VEC;
-      if (tail0 + tid < cnt) count(p[tail0 + tid]);
-      if (SEGP) {          // one REDUX pair per warp and key word, then one shared-memory atomic pair per warp
+        if (tid < head) count(p[tid], SUS);
+        const uint32_t tail0 = head + nvec * VEC;
+        if (tail0 + tid < cnt) count(p[tail0 + tid], SUS);
+      };
+      if (sus) count_tile(std::true_type{}); else count_tile(std::false_type{});
+      if (sus) {           // one REDUX pair per warp and key word, then one shared-memory atomic pair per warp
         const uint32_t o0 = __reduce_or_sync(0xffffffffu, (uint32_t)t_or), a0 = __reduce_and_sync(0xffffffffu, (uint32_t)t_and);
         uint32_t o1 = 0, a1 = 0xFFFFFFFFu;
         if (sizeof(K) == 8) {
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(HIST_THREADS) tile_hist_kernel(const __grid_co
         if ((tid & 31u) == 0) { atomicOr(&s_sor[0], o0); atomicAnd(&s_sand[0], a0); if (sizeof(K) == 8) { atomicOr(&s_sor[1], o1); atomicAnd(&s_sand[1], a1); } }
       }
       __syncthreads();
-      if (SEGP && tid == 0 && cnt != 0) {
+      if (sus && tid == 0 && cnt != 0) {
         atomicOr(&a.seg_or[td.seg], ((unsigned long long)s_sor[1] << 32) | s_sor[0]);
         atomicAnd(&a.seg_and[td.seg], ((unsigned long long)s_sand[1] << 32) | s_sand[0]);
       }

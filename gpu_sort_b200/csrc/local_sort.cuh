@@ -62,6 +62,7 @@ struct LsdSmem {
   uint32_t cnt[RADIX];                            // block counters of the unordered first pass
   uint32_t bin_start[RADIX];
   uint32_t scratch[8];
+  uint32_t red[4];                                // OR (low, high word) and AND (low, high word) of the bucket's keys
 };
 
 template <typename K, int VB, int THREADS, int IPT, int ALGO>
@@ -281,21 +282,53 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
       if (j < rows && idx < cnt) key[j] = twiddle_in<K>(key[j], tw);
     }
   }
-  if (passes == 0) {      // nothing to sort: (transformed) copy through the slot
+  // Constant-digit short circuit (cf. CUB's short_circuit, lsb/cub/cub/agent/agent_radix_sort_downsweep.cuh:701-724): a pass whose digit
+  // is the same for every key of the bucket changes nothing and is skipped.  Buckets of heavily duplicated inputs (one hot value, or
+  // a handful of values that differ in a few bits) otherwise pay a full ranking pass for every 8 bits that remain.
+  uint32_t active = 0;                                   // bit p: pass p (bits [lo + 8p, lo + 8p + 8)) has work to do
+  if (passes > 0) {
+    K kor = (K)0, kand = (K)~(K)0;
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const uint32_t idx = first_ordered ? obase + j * 32u : (uint32_t)j * THREADS + tid;
+      if (j < rows && idx < cnt) { kor |= key[j]; kand &= key[j]; }
+    }
+    if (tid == 0) { sm.red[0] = 0u; sm.red[1] = 0u; sm.red[2] = 0xFFFFFFFFu; sm.red[3] = 0xFFFFFFFFu; }
+    __syncthreads();
+    const uint32_t o0 = __reduce_or_sync(0xffffffffu, (uint32_t)kor), a0 = __reduce_and_sync(0xffffffffu, (uint32_t)kand);
+    uint32_t o1 = 0u, a1 = 0xFFFFFFFFu;
+    if (sizeof(K) == 8) {
+      o1 = __reduce_or_sync(0xffffffffu, (uint32_t)((unsigned long long)kor >> 32));
+      a1 = __reduce_and_sync(0xffffffffu, (uint32_t)((unsigned long long)kand >> 32));
+    }
+    if (lane == 0) {
+      atomicOr(&sm.red[0], o0); atomicAnd(&sm.red[2], a0);
+      if (sizeof(K) == 8) { atomicOr(&sm.red[1], o1); atomicAnd(&sm.red[3], a1); }
+    }
+    __syncthreads();
+    const unsigned long long diff = (((unsigned long long)sm.red[1] << 32) | sm.red[0]) ^ (((unsigned long long)sm.red[3] << 32) | sm.red[2]);
+    for (int p = 0; p < passes; ++p) {
+      const int shift = lo + 8 * p;
+      const uint32_t mask = (1u << (hi - shift < 8 ? hi - shift : 8)) - 1u;
+      if (((uint32_t)(diff >> shift) & mask) != 0u) active |= 1u << p;
+    }
+  }
+  if (active == 0) {      // nothing to sort: (transformed) copy through the slot
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) {
-      const uint32_t idx = obase + j * 32u;
+      const uint32_t idx = first_ordered ? obase + j * 32u : (uint32_t)j * THREADS + tid;
       if (j < rows && idx < cnt) { sk[idx] = key[j]; if (VB) sv[idx] = val[j]; }
     }
     __syncthreads();
     return;
   }
 
-  int p = 0;
   if (!STABLE) {
     // ---- first pass of an unstable sort: one shared-memory atomicAdd per key
-    const int shift = lo;
+    const int p0 = __ffs(active) - 1;
+    active &= active - 1u;
+    const int shift = lo + 8 * p0;
     const uint32_t mask = (1u << (hi - shift < 8 ? hi - shift : 8)) - 1u;
     if (tid < RADIX) sm.cnt[tid] = 0;
     __syncthreads();
@@ -315,8 +348,7 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
         if (VB) sv[q] = val[j];
       }
     __syncthreads();
-    p = 1;
-    if (p < passes) {
+    if (active) {
 #pragma unroll
       for (int j = 0; j < ROWS; ++j) {
         K k = (K)~(K)0;
@@ -328,8 +360,10 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
       }
     }
   }
-  for (; p < passes; ++p) {
+  while (active) {
     // ---- stable pass
+    const int p = __ffs(active) - 1;
+    active &= active - 1u;
     const int shift = lo + 8 * p;
     const uint32_t mask = (1u << (hi - shift < 8 ? hi - shift : 8)) - 1u;
     // (the match masks are all zero here: zeroed once at kernel start, and every row's leader clears the word it used)
@@ -380,7 +414,7 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
         if (q < cnt) { sk[q] = key[j]; if (VB) sv[q] = val[j]; }     // padding ranks after every real key
       }
     __syncthreads();
-    if (p + 1 < passes) {     // read back in warp-contiguous order for the next pass
+    if (active) {             // read back in warp-contiguous order for the next pass
 #pragma unroll
       for (int j = 0; j < ROWS; ++j) {
         K k = (K)~(K)0;

@@ -30,7 +30,7 @@ struct MsbCounters {            // one small zero-initialised block in the works
 static __global__ void msb_init_kernel(Seg* segs, MsbCounters* c, uint64_t n) {
   pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    segs[0].off = 0; segs[0].cnt = n;
+    segs[0].off = 0; segs[0].cnt = (uint32_t)n; segs[0].flags = 0;
     c->num_segs[0] = 1;
     c->key_or = 0ull; c->key_and = ~0ull;
   }
@@ -67,7 +67,7 @@ static __global__ void __launch_bounds__(256) seg_init_kernel(const __grid_const
     } else {
       const uint32_t slot = atomicAdd(&a.ctr->num_segs[0], 1u);
       if (slot >= a.max_segs) { atomicOr(&a.ctr->error, (uint32_t)ERR_SEG_OVERFLOW); continue; }
-      Seg sg; sg.off = (uint64_t)b; sg.cnt = cnt;
+      Seg sg; sg.off = (uint64_t)b; sg.cnt = (uint32_t)cnt; sg.flags = 0;
       a.segs[slot] = sg;
     }
   }
@@ -132,14 +132,14 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
     __syncwarp();
     if (a.last) continue;             // last digit: every sub-bucket is final after the scatter
 #if B200_SEG_CONST
-    if (a.seg_or != nullptr) {
+    if (a.seg_or != nullptr && (sg.flags & 1u)) {
       const int top = a.shift + a.nb;
       unsigned long long diff = a.seg_or[s] ^ a.seg_and[s];
       diff &= (top >= 64 ? ~0ull : ((1ull << top) - 1ull)) & ~((1ull << a.begin_bit) - 1ull);
       if (diff == 0ull) {
         // all keys of the segment are equal where it matters: this level's scatter copies it unchanged into out_buf (one digit);
         // nothing below needs sorting -- hand it to the on-chip kernel in capacity-sized chunks that just copy it to the final buffer
-        const uint32_t chunks = (uint32_t)((sg.cnt + a.local_cap - 1) / a.local_cap);
+        const uint32_t chunks = (uint32_t)(((uint64_t)sg.cnt + a.local_cap - 1) / a.local_cap);
         uint32_t cbase = 0;
         if (lane == 0) cbase = atomicAdd(a.num_copy_ptr, chunks);
         cbase = __shfl_sync(0xffffffffu, cbase, 0);
@@ -177,7 +177,7 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
         if (cd == 0) continue;
         if (cd > a.local_cap) {
           flush();
-          Seg ns; ns.off = s_off[w][d]; ns.cnt = cd;
+          Seg ns; ns.off = s_off[w][d]; ns.cnt = cd; ns.flags = cd == sg.cnt ? 1u : 0u;      // everything fell into one bucket: one repeated key?
           s_seg[w][nseg++] = ns;
         } else if (cd > a.merge_cap) {
           flush();
@@ -230,7 +230,7 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const S
   const uint32_t per = (ns + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t s0 = min(per * tid, ns), s1 = min(s0 + per, ns);
   uint32_t sum = 0;
-  for (uint32_t s = s0; s < s1; ++s) sum += (uint32_t)((segs[s].cnt + tile - 1) / tile);
+  for (uint32_t s = s0; s < s1; ++s) sum += (uint32_t)(((uint64_t)segs[s].cnt + tile - 1) / tile);
   uint32_t inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -258,7 +258,7 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const S
   uint32_t run = s_w[w] + inc - sum;
   for (uint32_t s = s0; s < s1; ++s) {
     tile_base[s] = run;
-    run += (uint32_t)((segs[s].cnt + tile - 1) / tile);
+    run += (uint32_t)(((uint64_t)segs[s].cnt + tile - 1) / tile);
   }
 }
 
@@ -273,7 +273,7 @@ static __global__ void fill_descs_kernel(const Seg* segs, const uint32_t* tile_b
       if (tile_base[mid] <= t) lo = mid; else hi = mid;
     }
     const Seg sg = segs[lo];
-    TileDesc td; td.seg = lo; td.tile_in_seg = t - tile_base[lo]; td.pad = 0;
+    TileDesc td; td.seg = lo; td.tile_in_seg = t - tile_base[lo]; td.pad = sg.flags;
     const uint64_t rel = (uint64_t)td.tile_in_seg * tile;
     td.off = sg.off + rel;
     td.cnt = (uint32_t)(sg.cnt - rel < (uint64_t)tile ? sg.cnt - rel : (uint64_t)tile);
