@@ -156,6 +156,76 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
       }
     }
 #endif
+    // Fast path (the common shape of a large uniform sort: 256 sub-buckets that are each too big to share an on-chip item with
+    // their neighbour): if no two neighbouring non-empty mergeable sub-buckets fit one item together, the greedy merge below
+    // would emit every sub-bucket on its own -- which 32 lanes do in 8 steps instead of one lane in 256.
+    {
+      bool pair = false;
+      uint32_t prev = 0;                                     // count of the previous non-empty digit if it may share an item, else 0
+      {
+        uint32_t mine = 0; bool has = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c[i]) { has = true; mine = c[i] <= a.merge_cap ? c[i] : 0u; }
+        const uint32_t hasmask = __ballot_sync(0xffffffffu, has) & ((1u << lane) - 1u);
+        const int src = hasmask ? 31 - __clz(hasmask) : 0;
+        const uint32_t got = __shfl_sync(0xffffffffu, mine, src);
+        prev = hasmask ? got : 0u;                           // (taken from the nearest lower lane that owns a non-empty digit)
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (c[i] == 0) continue;
+        const uint32_t cur = c[i] <= a.merge_cap ? c[i] : 0u;
+        if (prev && cur && prev + cur <= a.merge_cap) pair = true;
+        prev = cur;
+      }
+      if (__ballot_sync(0xffffffffu, pair) == 0u) {
+        uint32_t nl = 0, nm = 0, ng = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (c[i] == 0) continue;
+          if (c[i] > a.local_cap) ++ng;
+          else if (a.locals_small != nullptr && c[i] <= a.small_cap) ++nm;
+          else ++nl;
+        }
+        uint32_t il = nl, im = nm, ig = ng;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t tl = __shfl_up_sync(0xffffffffu, il, o), tm = __shfl_up_sync(0xffffffffu, im, o), tg = __shfl_up_sync(0xffffffffu, ig, o);
+          if (lane >= (unsigned)o) { il += tl; im += tm; ig += tg; }
+        }
+        uint32_t lb = 0, mb = 0, gb = 0;
+        if (lane == 31) {
+          if (il) lb = atomicAdd(a.num_locals_ptr, il);
+          if (im) mb = atomicAdd(a.num_small_ptr, im);
+          if (ig) gb = atomicAdd(a.num_next_ptr, ig);
+          if (lb + il > a.max_locals || mb + im > a.max_locals) atomicOr(a.error, (uint32_t)ERR_LOCAL_OVERFLOW);
+          if (gb + ig > a.max_segs) atomicOr(a.error, (uint32_t)ERR_SEG_OVERFLOW);
+        }
+        const uint32_t tl = __shfl_sync(0xffffffffu, il, 31), tm = __shfl_sync(0xffffffffu, im, 31), tg = __shfl_sync(0xffffffffu, ig, 31);
+        lb = __shfl_sync(0xffffffffu, lb, 31); mb = __shfl_sync(0xffffffffu, mb, 31); gb = __shfl_sync(0xffffffffu, gb, 31);
+        const bool okl = lb + tl <= a.max_locals, okm = mb + tm <= a.max_locals, okg = gb + tg <= a.max_segs;
+        uint32_t pl = lb + il - nl, pm = mb + im - nm, pg = gb + ig - ng;
+        uint64_t off = sg.off + (inc - sum);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t cd = c[i];
+          if (cd != 0) {
+            if (cd > a.local_cap) {
+              Seg ns; ns.off = off; ns.cnt = cd; ns.flags = cd == sg.cnt ? 1u : 0u;
+              if (okg) a.next_segs[pg] = ns;
+              ++pg;
+            } else {
+              LocalItem it; it.off = off; it.cnt = cd; it.nbits = (uint16_t)a.shift; it.src = (uint16_t)a.out_buf;
+              if (a.locals_small != nullptr && cd <= a.small_cap) { if (okm) a.locals_small[pm] = it; ++pm; }
+              else { if (okl) a.locals[pl] = it; ++pl; }
+            }
+          }
+          off += cd;
+        }
+        __syncwarp();
+        continue;
+      }
+    }
     // classify + merge, serial over the 256 digits (lane 0), staged in shared memory
     uint32_t nloc = 0, nseg = 0, nsml = 0, nmrg = 0;     // big items fill s_loc[w] from the front, small ones from the back;
     LocalItem* s_mrg = reinterpret_cast<LocalItem*>(&s_seg[w][0]);   // merged runs share s_seg[w] with the segments, from the back
