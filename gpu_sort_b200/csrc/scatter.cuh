@@ -551,14 +551,24 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
     }
     sm.geom[slot] = g;
   };
-  // digit owners (threads 0..255): counts, scan and destinations of the tile described by geom[slot] -> cnt / kptr / vptr[slot]
-  auto prepare = [&](int slot) {
+  // digit owners (threads 0..255): counts, scan and destinations of the tile described by geom[slot] -> cnt / kptr / vptr[slot].
+  // Two steps: prepare_load issues the global loads (their latency then hides behind the owner's share of the write-out),
+  // prepare_finish consumes them.
+  struct Prep { uint32_t c; uint64_t gstart; bool live; };
+  auto prepare_load = [&](int slot) -> Prep {
+    Prep p; p.c = 0; p.gstart = 0;
     const TileGeom g = sm.geom[slot];
-    if (g.tile >= num_tiles) return;                       // uniform over the 256 digit owners
-    const uint32_t c = a.tile_cnt[(uint64_t)g.tile * RADIX + tid];
+    p.live = g.tile < num_tiles;                           // uniform over the 256 digit owners
+    if (!p.live) return p;
+    p.c = a.tile_cnt[(uint64_t)g.tile * RADIX + tid];
     const uint32_t grp = g.tile / HIST_GROUP;
-    uint64_t gstart = a.bins[(uint64_t)g.seg * RADIX + tid] + a.tile_off[(uint64_t)g.tile * RADIX + tid];
-    if (g.tile - g.tile_in_seg < grp * HIST_GROUP) gstart += a.carry[(uint64_t)grp * RADIX + tid];     // the segment started in an earlier group
+    p.gstart = a.bins[(uint64_t)g.seg * RADIX + tid] + a.tile_off[(uint64_t)g.tile * RADIX + tid];
+    if (g.tile - g.tile_in_seg < grp * HIST_GROUP) p.gstart += a.carry[(uint64_t)grp * RADIX + tid];     // the segment started in an earlier group
+    return p;
+  };
+  auto prepare_finish = [&](int slot, const Prep& p) {
+    if (!p.live) return;
+    const uint32_t c = p.c; const uint64_t gstart = p.gstart;
     uint32_t inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -590,7 +600,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
     stage_tile(0, t0, td);
   }
   __syncthreads();
-  if (tid < RADIX) prepare(0);
+  if (tid < RADIX) prepare_finish(0, prepare_load(0));
   __syncthreads();
 
   for (uint32_t it = 0;; ++it) {
@@ -676,8 +686,8 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
         }
       }
       __syncthreads();          // reorder complete; geom[slot ^ 1] (written by the producer above) is visible
-      // ---- digit owners prepare the next tile while everybody writes this one out
-      if (tid < RADIX) prepare(slot ^ 1);
+      // ---- digit owners fetch the next tile's counts and destinations; the loads complete behind the write-out
+      Prep prep{}; if (tid < RADIX) prep = prepare_load(slot ^ 1);
       // ---- coalesced write-out: consecutive positions of one digit are consecutive output addresses
       K* __restrict__ kout = reinterpret_cast<K*>(a.keys_out);
       V* __restrict__ vout = reinterpret_cast<V*>(a.vals_out);
@@ -709,6 +719,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
           }
         }
       }
+      if (tid < RADIX) prepare_finish(slot ^ 1, prep);
     } else {
       // ---- keys: shared memory (TMA-staged) -> registers
       mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
@@ -765,8 +776,8 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
       for (int j = 0; j < IPT; ++j)
         if (full || tid + j * THREADS < cnt) { st[pos[j]] = key[j]; if (VB) vst[pos[j]] = val[j]; }
       __syncthreads();          // reorder complete; geom[slot ^ 1] (written by the producer above) is visible
-      // ---- digit owners prepare the next tile while everybody writes this one out
-      if (tid < RADIX) prepare(slot ^ 1);
+      // ---- digit owners fetch the next tile's counts and destinations; the loads complete behind the write-out
+      Prep prep{}; if (tid < RADIX) prep = prepare_load(slot ^ 1);
       // ---- coalesced write-out: consecutive positions of one digit are consecutive output addresses
       const uint32_t* __restrict__ go = sm.goff[slot];
       K* __restrict__ kout = reinterpret_cast<K*>(a.keys_out);
@@ -797,6 +808,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
           }
         }
       }
+      if (tid < RADIX) prepare_finish(slot ^ 1, prep);
     }
     __syncthreads();          // the slot (and cnt / kptr of this slot) may be overwritten from here on
     if (tid == PRODUCER) { tk_a = tk_b; td_a = td_b; }
@@ -871,13 +883,23 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
     }
     sm.geom[slot] = g;
   };
-  auto prepare = [&](int slot) {      // digit owners (threads 0..255)
+  // digit owners (threads 0..255), in two steps like scatter_fast_kernel: the global loads, then (behind the owner's share of the
+  // write-out) the scan and the shared-memory tables
+  struct Prep { uint32_t c; uint64_t gstart; bool live; };
+  auto prepare_load = [&](int slot) -> Prep {
+    Prep p; p.c = 0; p.gstart = 0;
     const TileGeom g = sm.geom[slot];
-    if (g.tile >= num_tiles) return;
-    const uint32_t c = a.tile_cnt[(uint64_t)g.tile * RADIX + tid];
+    p.live = g.tile < num_tiles;
+    if (!p.live) return p;
+    p.c = a.tile_cnt[(uint64_t)g.tile * RADIX + tid];
     const uint32_t grp = g.tile / HIST_GROUP;
-    uint64_t gstart = (PEER ? 0ull : a.bins[(uint64_t)g.seg * RADIX + tid]) + a.tile_off[(uint64_t)g.tile * RADIX + tid];
-    if (g.tile - g.tile_in_seg < grp * HIST_GROUP) gstart += a.carry[(uint64_t)grp * RADIX + tid];
+    p.gstart = (PEER ? 0ull : a.bins[(uint64_t)g.seg * RADIX + tid]) + a.tile_off[(uint64_t)g.tile * RADIX + tid];
+    if (g.tile - g.tile_in_seg < grp * HIST_GROUP) p.gstart += a.carry[(uint64_t)grp * RADIX + tid];
+    return p;
+  };
+  auto prepare_finish = [&](int slot, const Prep& p) {
+    if (!p.live) return;
+    const uint32_t c = p.c; const uint64_t gstart = p.gstart;
     uint32_t inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -930,7 +952,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
     if (VB) sm.dstv[PEER ? tid : 0] = a.dst_vals[tid];
   }
   __syncthreads();
-  if (tid < RADIX) prepare(0);
+  if (tid < RADIX) prepare_finish(0, prepare_load(0));
   __syncthreads();
 
   for (uint32_t it = 0;; ++it) {
@@ -1011,7 +1033,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
       }
     }
     __syncthreads();          // (3) reorder complete; geom[slot ^ 1] is visible
-    if (tid < RADIX) prepare(slot ^ 1);
+    Prep prep{}; if (tid < RADIX) prep = prepare_load(slot ^ 1);      // (the loads complete behind the write-out)
     {                         // the per-warp counters are free again: zero them for the next tile
       uint4* zc = reinterpret_cast<uint4*>(sm.wcnt);
       for (int i = tid; i < WARPS * RADIX / 8; i += THREADS) zc[i] = make_uint4(0, 0, 0, 0);
@@ -1041,6 +1063,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
         }
       }
     }
+    if (tid < RADIX) prepare_finish(slot ^ 1, prep);
     __syncthreads();          // (4)
     if (tid == PRODUCER) { tk_a = tk_b; td_a = td_b; }
   }
