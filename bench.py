@@ -538,6 +538,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS), help="default: cfg2 on one GPU, cfg5 on several")
     ap.add_argument("--logn", type=int, default=0, help="override log2(keys per GPU)")
+    ap.add_argument("--dist", default=None, help="override the workload's key distribution: uniform|entropy|zipf_rank|zipf_hash|sorted|reverse|constant")
+    ap.add_argument("--param", type=int, default=0, help="distribution parameter (entropy: number of AND rounds)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="single GPU: skip the short cfg3 / cfg4 runs carried in the default line")
@@ -548,6 +550,10 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload is None:
         args.workload = "cfg2" if world == 1 else "cfg5"
+    if args.dist is not None:       # the skew sweep of config 4: same sizes and types, another key distribution
+        w = list(WORKLOADS[args.workload]); w[4] = args.dist; w[5] = args.param
+        w[7] = w[7].replace("Zipf-skewed", f"{args.dist}" + (f"({args.param})" if args.param else "")).replace("uniform", args.dist)
+        WORKLOADS[args.workload] = tuple(w)
 
     if args.impl == "reference":
         if rank != 0:

@@ -236,8 +236,7 @@ __global__ void __launch_bounds__(THREADS, OCC) bitmap_sort_kernel(const __grid_
       if (tid == 0) sm.nextra = 0;
     }
     if (!sorted && tid == 0) {
-      const uint32_t o = atomicAdd(a.num_overflow_ptr, 1u);
-      if (o < a.max_items) a.overflow[o] = it; else atomicOr(a.error_ptr, 2u);
+      hand_back(a, it);
     }
 
     // ---- phase D: the bucket sits at sk[aoff ..): shared-memory vector v and output vector v cover the same elements

@@ -363,8 +363,12 @@ __global__ void __launch_bounds__(THREADS, OCC) rank_sort_kernel(const __grid_co
     if (!sorted && tid == 0) {
       // too many copies of some value for this variant: the dense variant takes the bucket if it can, the LSD kernel otherwise
       const bool to_dense = !DENSE && a.dense != nullptr && nb <= RANK_DENSE_BITS;
-      const uint32_t o = atomicAdd(to_dense ? a.num_dense_ptr : a.num_overflow_ptr, 1u);
-      if (o < a.max_items) (to_dense ? a.dense : a.overflow)[o] = it; else atomicOr(a.error_ptr, 2u);
+      if (to_dense) {
+        const uint32_t o = atomicAdd(a.num_dense_ptr, 1u);
+        if (o < a.max_items) a.dense[o] = it; else atomicOr(a.error_ptr, 2u);
+      } else {
+        hand_back(a, it);
+      }
     }
 
     // ---- D: shared-memory vector v and output vector v cover the same elements, both 16-byte aligned

@@ -31,6 +31,7 @@ struct LocalArgs {
   const LocalItem* items; const uint32_t* num_items_ptr;
   uint32_t max_items;                    // capacity of every work list (a count above it means the list overflowed: the error flag is up)
   LocalItem* overflow; uint32_t* num_overflow_ptr;     // ALGO_COUNT / bitmap sort: buckets they could not take
+  LocalItem* overflow_small; uint32_t* num_overflow_small_ptr; uint32_t overflow_small_cap;   // ... those of at most overflow_small_cap keys (nullptr: all to `overflow`)
   uint32_t* error_ptr;                   // MsbCounters::error
   LocalItem* dense; uint32_t* num_dense_ptr;           // rank sort: buckets passed on to its dense variant (nullptr: none)
   int tw_in;                             // keys still in caller form (single-tile sorts)
@@ -255,7 +256,12 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
 // ---------------------------------------------------------------------------------------------------------------
 // ALGO_LSD.  On return the sorted bucket is at sk[0..cnt), sv[0..cnt).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename K, int VB, int THREADS, int ROWS, bool STABLE>
+// SKEW (compile time): the bucket was handed back by a one-shot kernel, i.e. its digits are skewed (heavy duplicates, low-entropy
+// bits).  Same-address shared-memory atomics serialise (measured 8-10 wavefronts per instruction on such buckets,
+// profiles/r02_lsd_entropy2.txt), so the lanes of a warp that hold the row's HOT digit are found with one vote and share one
+// atomic / one counter update; the other lanes rank as usual.  Uniform digits are better off without the extra votes (measured:
+// +25 % on the merged runs of a 2^24-key sort), hence two instantiations.
+template <typename K, int VB, int THREADS, int ROWS, bool STABLE, bool SKEW = false>
 __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValType<VB>::type* __restrict__ sv, uint32_t skew, uint32_t vskew,
                                               uint32_t cnt, int lo, int hi, bool tw_in, const Twiddle& tw, LsdSmem<THREADS>& sm) {
   using V = typename ValType<VB>::type;
@@ -332,9 +338,30 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
     const uint32_t mask = (1u << (hi - shift < 8 ? hi - shift : 8)) - 1u;
     if (tid < RADIX) sm.cnt[tid] = 0;
     __syncthreads();
+    if (!SKEW) {
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j)
-      if (j < rows && (uint32_t)j * THREADS + tid < cnt) pos[j] = atomicAdd(&sm.cnt[digit_of<K>(key[j], shift, mask)], 1u);
+      for (int j = 0; j < ROWS; ++j)
+        if (j < rows && (uint32_t)j * THREADS + tid < cnt) pos[j] = atomicAdd(&sm.cnt[digit_of<K>(key[j], shift, mask)], 1u);
+    } else {
+      unsigned hot_d = 0;
+      const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j)
+        if (j < rows) {      // block-uniform
+          const bool v = (uint32_t)j * THREADS + tid < cnt;
+          const unsigned d = digit_of<K>(key[j], shift, mask);
+          const unsigned hot = __ballot_sync(0xffffffffu, v && d == hot_d);      // one atomic for all lanes on the warp's hot digit
+          if (v && d == hot_d) {
+            unsigned b = 0;
+            if ((hot & lt) == 0u) b = atomicAdd(&sm.cnt[d], (uint32_t)__popc(hot));
+            pos[j] = __shfl_sync(hot, b, __ffs(hot) - 1) + __popc(hot & lt);
+          } else if (v) {
+            pos[j] = atomicAdd(&sm.cnt[d], 1u);
+          }
+          // a small hot group: try the digit of the row's first valid lane next
+          if (__popc(hot) < 8) { const unsigned vm = __ballot_sync(0xffffffffu, v); hot_d = vm ? __shfl_sync(0xffffffffu, d, __ffs(vm) - 1) : hot_d; }
+        }
+    }
     __syncthreads();
     const uint32_t total = tid < RADIX ? sm.cnt[tid] : 0u;
     const uint32_t excl = block_excl_scan_256(total, sm.scratch);
@@ -372,20 +399,24 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
     __syncthreads();
     uint16_t* wc = sm.wcnt + w * RADIX;
     const unsigned lt = (1u << lane) - 1u, lbit = 1u << lane;
+    unsigned hot_d = 0;        // SKEW: the most frequent digit of the warp's previous row
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) {
       if (j < rows) {        // block-uniform
         uint32_t* wm = sm.match[j & 1] + w * RADIX;
         const unsigned d = digit_of<K>(key[j], shift, mask);       // padding keys (all ones) sit last and rank last
-        atomicOr(&wm[d], lbit);
+        const bool is_hot = SKEW && d == hot_d;
+        const unsigned hot = SKEW ? __ballot_sync(0xffffffffu, is_hot) : 0u;
+        if (!is_hot) atomicOr(&wm[d], lbit);
         __syncwarp();
-        const unsigned peers = wm[d];
+        const unsigned peers = is_hot ? hot : wm[d];
         __syncwarp();
         const unsigned below = __popc(peers & lt);
         unsigned b = 0;
-        if (below == 0) { b = wc[d]; wc[d] = (uint16_t)(b + __popc(peers)); wm[d] = 0; }
+        if (below == 0) { b = wc[d]; wc[d] = (uint16_t)(b + __popc(peers)); if (!is_hot) wm[d] = 0; }
         b = __shfl_sync(0xffffffffu, b, __ffs(peers) - 1);
         pos[j] = b + below;
+        if (SKEW) hot_d = __reduce_max_sync(0xffffffffu, ((unsigned)__popc(peers) << 8) | d) & 0xFFu;
       }
     }
     __syncthreads();
@@ -438,7 +469,16 @@ __device__ __forceinline__ void lsd_sort_item(K* __restrict__ sk, typename ValTy
 #ifndef B200_LOCAL_VEC_OUT
 #define B200_LOCAL_VEC_OUT 1
 #endif
-template <typename K, int VB, int THREADS, int IPT, int ALGO, bool STABLE>
+// A bucket the one-shot kernels could not take (heavy duplicates, skewed bits) goes to the LSD kernels: by size, because a small bucket
+// in the large configuration pays that configuration's fixed cost per pass (24 warps' counters, four block barriers) for a handful of rows.
+__device__ __forceinline__ void hand_back(const LocalArgs& a, const LocalItem& it) {
+  const bool small = a.overflow_small != nullptr && it.cnt <= a.overflow_small_cap;
+  const uint32_t o = atomicAdd(small ? a.num_overflow_small_ptr : a.num_overflow_ptr, 1u);
+  if (o < a.max_items) (small ? a.overflow_small : a.overflow)[o] = it; else atomicOr(a.error_ptr, 2u);
+}
+
+// SKEW: the launch serves the handed-back buckets, whose digits are known to be skewed (see lsd_sort_item).
+template <typename K, int VB, int THREADS, int IPT, int ALGO, bool STABLE, bool SKEW = false>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 ? ((VB == 0 && ALGO == ALGO_LSD) ? 3 : B200_LOCAL_OCC384) : (sizeof(LocalSmem<K, VB, THREADS, IPT, ALGO>) <= 113 * 1024 && THREADS <= 768) ? 2 : 1)) local_sort_kernel(const __grid_constant__ LocalArgs a) {
   pdl_wait();
   using V = typename ValType<VB>::type;
@@ -514,12 +554,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 
       aoff = vec ? (uint32_t)((reinterpret_cast<uintptr_t>(keys_out + it.off) & 15u) / sizeof(K)) : 0u;
       sorted = count_sort_item<K, VB, THREADS, IPT, STABLE>(sk, sv, sm.origin, skew, vskew, cnt, lo, hi, a.tw_in != 0, a.tw,
                                                              *reinterpret_cast<CountSmem<THREADS, CountBits<K, VB>::value>*>(&sm.rank), aoff);
-      if (!sorted && tid == 0) {
-        const uint32_t o = atomicAdd(a.num_overflow_ptr, 1u);
-        if (o < a.max_items) a.overflow[o] = it; else atomicOr(a.error_ptr, 2u);
-      }
+      if (!sorted && tid == 0) hand_back(a, it);
     } else {
-      lsd_sort_item<K, VB, THREADS, IPT, STABLE>(sk, sv, skew, vskew, cnt, lo, hi, a.tw_in != 0, a.tw, *reinterpret_cast<LsdSmem<THREADS>*>(&sm.rank));
+      lsd_sort_item<K, VB, THREADS, IPT, STABLE, SKEW>(sk, sv, skew, vskew, cnt, lo, hi, a.tw_in != 0, a.tw, *reinterpret_cast<LsdSmem<THREADS>*>(&sm.rank));
     }
 
     // ---- coalesced write-out of the sorted bucket

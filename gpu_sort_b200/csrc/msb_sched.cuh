@@ -25,6 +25,7 @@ struct MsbCounters {            // one small zero-initialised block in the works
   unsigned long long key_or, key_and;     // OR / AND of all transformed keys (level-0 histogram): bits where they agree are constant
   uint32_t probe_single, num_dense;       // (probe_single is read back together with key_or / key_and) the level-0 histogram has one non-empty bucket;
                                           // num_dense: work list of the dense rank sort (large buckets whose keys crowd their cells)
+  uint32_t num_overflow_small, pad_;      // handed-back buckets small enough for the 256-thread LSD configuration
 };
 
 static __global__ void msb_init_kernel(Seg* segs, MsbCounters* c, uint64_t n) {

@@ -509,6 +509,7 @@ struct FastSmem {
   alignas(8) uint64_t bar[2];
   TileGeom geom[2];
   uint32_t skewed[2];
+  uint32_t hot[2];                  // a digit that holds more than an eighth of the tile (the largest such digit number), when skewed
 };
 
 template <typename K, int VB, int THREADS, int IPT, int OCC>
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
       if (lane >= (unsigned)o) inc += t;
     }
     if (lane == 31) sm.scratch[slot][w] = inc;
-    if (tid == 0) sm.skewed[slot] = 0;
+    if (tid == 0) { sm.skewed[slot] = 0; sm.hot[slot] = 0; }
     asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight digit-owner warps only
     uint32_t woff = 0;
 #pragma unroll
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
     const uint32_t excl = woff + inc - c;
     sm.cnt[slot][tid] = VB == 0 ? smem_u32(&sm.stage[slot][0]) + excl * (uint32_t)sizeof(K) : excl;      // keys-only: shared ADDRESS of the digit's first slot
     sm.goff[slot][tid] = (uint32_t)gstart - excl;          // n < 2^32: indices wrap correctly in 32 bits
-    if (c > (uint32_t)TILE / 4) sm.skewed[slot] = 1;         // dominant digit: aggregate same-digit warps (see scatter_tile)
+    if (c > (uint32_t)TILE / 8) { sm.skewed[slot] = 1; atomicMax(&sm.hot[slot], tid); }      // a dominant digit: its lanes share one atomic per warp and row
   };
 
   uint32_t tk_a = 0, tk_b = 0;
@@ -658,15 +659,18 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
             if (tid + j * THREADS < cnt) pos[j] = atoms_add(ctr_base + digit_of<K>(key[j], shift, mask) * 4u, (uint32_t)sizeof(K));
         }
       } else {
+        // a dominant digit: the lanes holding it share ONE atomic per warp and row (same-address atomics serialise)
+        unsigned hot_d = sm.hot[slot];
+        const unsigned lt = (1u << lane) - 1u;
   #pragma unroll
         for (int j = 0; j < IPT; ++j) {
           const bool v = tid + j * THREADS < cnt;
           const unsigned d = digit_of<K>(key[j], shift, mask);
-          const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
-          if (__all_sync(0xffffffffu, v && d == d0)) {
+          const unsigned hot = __ballot_sync(0xffffffffu, v && d == hot_d);
+          if (v && d == hot_d) {
             unsigned b = 0;
-            if (lane == 0) b = atoms_add(ctr_base + d0 * 4u, 32u * (uint32_t)sizeof(K));
-            pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane * (uint32_t)sizeof(K);
+            if ((hot & lt) == 0u) b = atoms_add(ctr_base + d * 4u, (uint32_t)__popc(hot) * (uint32_t)sizeof(K));
+            pos[j] = __shfl_sync(hot, b, __ffs(hot) - 1) + (uint32_t)__popc(hot & lt) * (uint32_t)sizeof(K);
           } else if (v) {
             pos[j] = atoms_add(ctr_base + d * 4u, (uint32_t)sizeof(K));
           }
@@ -750,15 +754,17 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_fast_kernel(const __grid
             if (tid + j * THREADS < cnt) pos[j] = atomicAdd(&ctr[digit_of<K>(key[j], shift, mask)], 1u);
         }
       } else {
+        unsigned hot_d = sm.hot[slot];
+        const unsigned lt = (1u << lane) - 1u;
   #pragma unroll
         for (int j = 0; j < IPT; ++j) {
           const bool v = tid + j * THREADS < cnt;
           const unsigned d = digit_of<K>(key[j], shift, mask);
-          const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
-          if (__all_sync(0xffffffffu, v && d == d0)) {
+          const unsigned hot = __ballot_sync(0xffffffffu, v && d == hot_d);
+          if (v && d == hot_d) {
             unsigned b = 0;
-            if (lane == 0) b = atomicAdd(&ctr[d0], 32u);
-            pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane;
+            if ((hot & lt) == 0u) b = atomicAdd(&ctr[d], (uint32_t)__popc(hot));
+            pos[j] = __shfl_sync(hot, b, __ffs(hot) - 1) + (uint32_t)__popc(hot & lt);
           } else if (v) {
             pos[j] = atomicAdd(&ctr[d], 1u);
           }
@@ -998,19 +1004,25 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
     {
       uint16_t* wc = sm.wcnt + w * RADIX;
       const unsigned lt = (1u << lane) - 1u, lbit = 1u << lane;
+      // the lanes on the row's hot digit (the most frequent digit of the warp's previous row) meet through one vote instead of
+      // same-address atomics, which serialise on skewed digits (local_sort.cuh, lsd_sort_item)
+      unsigned hot_d = 0;
 #pragma unroll
       for (int j = 0; j < IPT; ++j) {
         uint32_t* wm = sm.match[j & 1] + w * RADIX;
         const unsigned d = digit_of<K>(key[j], shift, mask);
-        atomicOr(&wm[d], lbit);
+        const bool is_hot = d == hot_d;
+        const unsigned hot = __ballot_sync(0xffffffffu, is_hot);
+        if (!is_hot) atomicOr(&wm[d], lbit);
         __syncwarp();
-        const unsigned peers = wm[d];
+        const unsigned peers = is_hot ? hot : wm[d];
         __syncwarp();
         const unsigned below = __popc(peers & lt);
         unsigned b = 0;
-        if (below == 0) { b = wc[d]; wc[d] = (uint16_t)(b + __popc(peers)); wm[d] = 0; }
+        if (below == 0) { b = wc[d]; wc[d] = (uint16_t)(b + __popc(peers)); if (!is_hot) wm[d] = 0; }
         b = __shfl_sync(0xffffffffu, b, __ffs(peers) - 1);
         pos[j] = b + below;
+        hot_d = __reduce_max_sync(0xffffffffu, ((unsigned)__popc(peers) << 8) | d) & 0xFFu;
       }
     }
     __syncthreads();          // (1) all per-warp counts are final; every thread holds its keys and values in registers

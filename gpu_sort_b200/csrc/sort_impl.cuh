@@ -166,12 +166,12 @@ inline cudaError_t launch_scatter(const ScatterArgs& a, uint32_t tiles_hint, cud
   return cudaGetLastError();
 }
 
-template <typename K, int VB, int ALGO, bool STABLE, bool SMALL = false>
+template <typename K, int VB, int ALGO, bool STABLE, bool SMALL = false, bool SKEW = false>
 inline cudaError_t launch_local(const LocalArgs& a, uint32_t items_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
   constexpr int THREADS = SMALL ? C::SMALL_THREADS : C::LOCAL_THREADS;
   constexpr int IPT = SMALL ? C::SMALL_IPT : C::LOCAL_IPT;
-  auto kernel = local_sort_kernel<K, VB, THREADS, IPT, ALGO, STABLE>;
+  auto kernel = local_sort_kernel<K, VB, THREADS, IPT, ALGO, STABLE, SKEW>;
   constexpr size_t smem = sizeof(LocalSmem<K, VB, THREADS, IPT, ALGO>);
   static_assert(smem <= 227 * 1024, "local sort exceeds the 227 KB shared-memory limit");
   static int grids[MAX_DEVICES] = {};
@@ -276,7 +276,7 @@ struct Carver {      // sub-allocates the caller's temporary storage, 256-byte a
 // ===============================================================================================================
 struct MsdWorkspace {
   MsbCounters* ctr; Seg* segs0; Seg* segs1; uint32_t* tile_base; TileDesc* descs; uint32_t* seg_hist; uint64_t* bins;
-  uint32_t* tile_off; uint16_t* tile_cnt; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[6];   // LSD list, counting list, overflow, small-bucket LSD list, rank list, dense rank list
+  uint32_t* tile_off; uint16_t* tile_cnt; uint32_t* group_tail; uint32_t* group_flag; uint32_t* carry; LocalItem* locals[7];   // LSD list, counting list, overflow, small-bucket LSD list, rank list, dense rank list, small overflow
   uint32_t max_segs, max_tiles, max_locals, max_groups;
   unsigned long long* seg_or; unsigned long long* seg_and;      // B200_SEG_CONST: per-segment OR / AND of the keys
 };
@@ -301,7 +301,7 @@ inline void msd_carve(Carver& cv, uint64_t n, MsdWorkspace& w) {
   w.group_tail = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
   w.group_flag = cv.take<uint32_t>(w.max_groups);
   w.carry = cv.take<uint32_t>((size_t)w.max_groups * RADIX);
-  for (int i = 0; i < 6; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
+  for (int i = 0; i < 7; ++i) w.locals[i] = cv.take<LocalItem>(w.max_locals);
 #if B200_SEG_CONST
   w.seg_or = cv.take<unsigned long long>(w.max_segs);
   w.seg_and = cv.take<unsigned long long>(w.max_segs);
@@ -379,6 +379,7 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
   for (int i = 0; i < 3; ++i) { la.keys[i] = bufk[i < nbuf ? i : 0]; la.vals[i] = bufv[i < nbuf ? i : 0]; }
   la.items = w.locals[0]; la.num_items_ptr = &ctr->num_locals[0];
   la.overflow = w.locals[2]; la.num_overflow_ptr = &ctr->num_overflow;
+  la.overflow_small = w.locals[6]; la.num_overflow_small_ptr = &ctr->num_overflow_small; la.overflow_small_cap = C::SMALL_CAP;
   la.max_items = w.max_locals; la.error_ptr = &ctr->error;
   // the sort covers the whole key: buckets whose undecided bits are equal hold equal keys, so the on-chip sort may rebuild keys from cells
   const bool whole_key = begin_bit == 0 && end_bit == (int)sizeof(K) * 8;
@@ -537,7 +538,9 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
         if (use_bitmap) B200_CHECK((launch_bitmap<K, VB>(la, w.max_locals, s)));
       }
       la.items = w.locals[2]; la.num_items_ptr = &ctr->num_overflow;       // buckets those kernels handed back (heavy duplicates): LSD passes instead
-      B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED>(la, w.max_locals, s)));
+      B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, false, true>(la, w.max_locals, s)));
+      la.items = w.locals[6]; la.num_items_ptr = &ctr->num_overflow_small;      // ... the small ones in the 256-thread configuration
+      B200_CHECK((launch_local<K, VB, ALGO_LSD, ORDERED, true, true>(la, w.max_locals, s)));
     }
     if (!probe) break;
     B200_CHECK(cudaEventSynchronize(probe_event()));
