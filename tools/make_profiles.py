@@ -17,6 +17,8 @@ def family(name):
     if "scatter_kernel" in name and len(args) >= 7:
         mode, ord_ = args[5], args[6]
         return {"0": "scatter_stable" if ord_ in ("1", "true") else "scatter", "1": "scatter_onesweep", "2": "range_partition"}.get(mode, "scatter")
+    if "rank_sort_kernel" in name: return "local_sort_rank_dense" if (len(args) >= 7 and args[6] in ("1", "true")) else "local_sort_rank"
+    if "bitmap_sort_kernel" in name: return "local_sort_bitmap"
     if "local_sort_kernel" in name and len(args) >= 6:
         return "local_sort_count" if args[4] == "1" else "local_sort_lsd"
     if "tile_hist_kernel" in name: return "tile_hist"
