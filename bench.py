@@ -254,9 +254,12 @@ def run_ours_single(args, wl):
 
 def extra_workloads(args):
     """BASELINE's metric reads "keys/pairs": the default line also carries the pairs config (cfg3) and the skewed 64-bit config
-    (cfg4, Zipf-hashed keys) as short runs with their own roofline figures (full lines: bench.py --workload cfg3 | cfg4)."""
+    (cfg4, Zipf-hashed keys) as short runs with their own roofline figures (full lines: bench.py --workload cfg3 | cfg4), and the
+    single-GPU point of the multi-GPU weak-scaling series (cfg5)."""
     out = {}
-    for name in ("cfg3", "cfg4"):
+    # cfg5 here = ONE GPU's share of the multi-GPU config (2^29 pairs, stable): the N = 1 point of the weak-scaling series that
+    # `bench.py --gpus N` measures on N > 1 GPUs (those lines carry the same figure as `single_gpu_same_workload`)
+    for name in ("cfg3", "cfg4", "cfg5"):
         sub = argparse.Namespace(**vars(args))
         sub.workload = name; sub.steps = max(3, min(args.steps, 5)); sub.warmup = 3; sub.no_cpu = True; sub.no_e2e = True; sub.logn = 0
         try:

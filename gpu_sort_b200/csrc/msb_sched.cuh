@@ -92,6 +92,12 @@ struct ClassifyArgs {
   int nb;                       // width of this level's digit (8, or less on the last level of a bit sub-range)
   int last;                     // no bits remain below this digit: every sub-bucket is final after the scatter
   uint32_t local_cap, merge_cap;
+  uint32_t merge_small;         // only sub-buckets of at most this many keys are merged with their neighbours (<= merge_cap): two
+                                // half-capacity buckets merged cost one more pass over all their keys, apart they cost nothing extra
+  uint32_t small_max;           // a bucket that stands alone goes to `locals_small` only below this size (<= small_cap): with more than 8 bits
+                                // left the one-shot kernel behind `locals` beats two passes of the small LSD configuration from here on
+  int dense_to_merged;          // 1: at most 8 bits remain below this digit -- a bucket that stands alone needs ONE counting pass of
+                                // the LSD kernel and goes to `locals_merged`, not to the one-shot list `locals` (its cells would overflow)
   uint32_t out_buf;             // ping-pong buffer the level scatters into
   // B200_SEG_CONST: per-segment OR / AND of the keys (nullptr: off) -- a segment whose keys agree on every bit still to be
   // sorted, [begin_bit, shift + nb), is finished by copy-through items (nbits = begin_bit: zero on-chip passes) in the LSD list
@@ -166,7 +172,7 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
       {
         uint32_t mine = 0; bool has = false;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (c[i]) { has = true; mine = c[i] <= a.merge_cap ? c[i] : 0u; }
+        for (int i = 0; i < 8; ++i) if (c[i]) { has = true; mine = c[i] <= a.merge_small ? c[i] : 0u; }
         const uint32_t hasmask = __ballot_sync(0xffffffffu, has) & ((1u << lane) - 1u);
         const int src = hasmask ? 31 - __clz(hasmask) : 0;
         const uint32_t got = __shfl_sync(0xffffffffu, mine, src);
@@ -175,17 +181,20 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (c[i] == 0) continue;
-        const uint32_t cur = c[i] <= a.merge_cap ? c[i] : 0u;
+        const uint32_t cur = c[i] <= a.merge_small ? c[i] : 0u;
         if (prev && cur && prev + cur <= a.merge_cap) pair = true;
         prev = cur;
       }
       if (__ballot_sync(0xffffffffu, pair) == 0u) {
+        // single buckets of the one-shot list go to the LSD list instead when one counting pass finishes them (dense_to_merged)
+        LocalItem* const single_list = (a.dense_to_merged && a.locals_merged != nullptr) ? a.locals_merged : a.locals;
+        uint32_t* const single_cnt = (a.dense_to_merged && a.locals_merged != nullptr) ? a.num_merged_ptr : a.num_locals_ptr;
         uint32_t nl = 0, nm = 0, ng = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (c[i] == 0) continue;
           if (c[i] > a.local_cap) ++ng;
-          else if (a.locals_small != nullptr && c[i] <= a.small_cap) ++nm;
+          else if (a.locals_small != nullptr && c[i] <= a.small_max) ++nm;
           else ++nl;
         }
         uint32_t il = nl, im = nm, ig = ng;
@@ -196,7 +205,7 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
         }
         uint32_t lb = 0, mb = 0, gb = 0;
         if (lane == 31) {
-          if (il) lb = atomicAdd(a.num_locals_ptr, il);
+          if (il) lb = atomicAdd(single_cnt, il);
           if (im) mb = atomicAdd(a.num_small_ptr, im);
           if (ig) gb = atomicAdd(a.num_next_ptr, ig);
           if (lb + il > a.max_locals || mb + im > a.max_locals) atomicOr(a.error, (uint32_t)ERR_LOCAL_OVERFLOW);
@@ -217,8 +226,8 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
               ++pg;
             } else {
               LocalItem it; it.off = off; it.cnt = cd; it.nbits = (uint16_t)a.shift; it.src = (uint16_t)a.out_buf;
-              if (a.locals_small != nullptr && cd <= a.small_cap) { if (okm) a.locals_small[pm] = it; ++pm; }
-              else { if (okl) a.locals[pl] = it; ++pl; }
+              if (a.locals_small != nullptr && cd <= a.small_max) { if (okm) a.locals_small[pm] = it; ++pm; }
+              else { if (okl) single_list[pl] = it; ++pl; }
             }
           }
           off += cd;
@@ -237,8 +246,8 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
         if (pend_n) {
           LocalItem it; it.off = pend_off; it.cnt = pend_sum;
           it.nbits = (uint16_t)(pend_n > 1 ? a.shift + a.nb : a.shift); it.src = (uint16_t)a.out_buf;
-          if (a.locals_small != nullptr && it.cnt <= a.small_cap) s_loc[w][RADIX - 1 - nsml++] = it;
-          else if (a.locals_merged != nullptr && pend_n > 1) s_mrg[RADIX - 1 - nmrg++] = it;
+          if (a.locals_small != nullptr && it.cnt <= (pend_n > 1 ? a.small_cap : a.small_max)) s_loc[w][RADIX - 1 - nsml++] = it;
+          else if (a.locals_merged != nullptr && (pend_n > 1 || a.dense_to_merged)) s_mrg[RADIX - 1 - nmrg++] = it;
           else s_loc[w][nloc++] = it;
           pend_n = 0; pend_sum = 0;
         }
@@ -250,10 +259,12 @@ static __global__ void __launch_bounds__(CLS_WARPS * 32) classify_kernel(const _
           flush();
           Seg ns; ns.off = s_off[w][d]; ns.cnt = cd; ns.flags = cd == sg.cnt ? 1u : 0u;      // everything fell into one bucket: one repeated key?
           s_seg[w][nseg++] = ns;
-        } else if (cd > a.merge_cap) {
+        } else if (cd > a.merge_small) {     // stands alone
           flush();
           LocalItem it; it.off = s_off[w][d]; it.cnt = cd; it.nbits = (uint16_t)a.shift; it.src = (uint16_t)a.out_buf;
-          if (a.locals_small != nullptr && cd <= a.small_cap) s_loc[w][RADIX - 1 - nsml++] = it; else s_loc[w][nloc++] = it;
+          if (a.locals_small != nullptr && cd <= a.small_max) s_loc[w][RADIX - 1 - nsml++] = it;
+          else if (a.locals_merged != nullptr && a.dense_to_merged) s_mrg[RADIX - 1 - nmrg++] = it;
+          else s_loc[w][nloc++] = it;
         } else {
           if (pend_n && pend_sum + cd > a.merge_cap) flush();
           if (pend_n == 0) pend_off = s_off[w][d];

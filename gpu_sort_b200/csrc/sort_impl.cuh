@@ -217,6 +217,9 @@ inline cudaError_t launch_bitmap(const LocalArgs& a, uint32_t items_hint, cudaSt
 #ifndef B200_RANK_OCC0
 #define B200_RANK_OCC0 0
 #endif
+#ifndef B200_RANK_MIN
+#define B200_RANK_MIN 1537        // smallest single bucket (9-16 bits left) routed to the rank kernel instead of the small LSD configuration
+#endif
 template <typename K, int VB, bool STABLE, bool DENSE = false>
 inline cudaError_t launch_rank(const LocalArgs& a, uint32_t items_hint, cudaStream_t s) {
   using C = Cfg<K, VB>;
@@ -486,6 +489,17 @@ cudaError_t msd_sort_run(const MsdWorkspace& w, void* const bufk[3], void* const
       if (count_big || big_special) { ca.locals_merged = w.locals[ALGO_LSD]; ca.num_merged_ptr = &ctr->num_locals[ALGO_LSD]; }   // merged runs need LSD passes
       ca.error = &ctr->error; ca.shift = shift; ca.nb = nb; ca.last = (shift == begin_bit) ? 1 : 0;
       ca.local_cap = C::LOCAL_CAP; ca.merge_cap = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP : C::MERGE_CAP;
+      // LSD levels: only small sub-buckets are merged (a merged run pays one more 8-bit pass over all of its keys); a bucket that
+      // stands alone with at most 8 bits left is one counting pass of the LSD kernel, not a job for the one-shot kernels
+      ca.merge_small = (list == ALGO_LSD) ? (uint32_t)C::LOCAL_CAP / 8u : ca.merge_cap;
+      ca.dense_to_merged = (list == ALGO_LSD && shift - begin_bit <= 8) ? 1 : 0;
+      // single buckets below the small configuration's capacity: with 9-16 bits left the rank kernel (one step) takes them from
+      // B200_RANK_MIN keys on (measured); below that, and with at most 8 bits left, the small LSD configuration
+      ca.small_max = C::SMALL_CAP;
+      if (big_special && use_rank && !ca.dense_to_merged) {
+        static const uint32_t rank_min = []() { const char* e = getenv("B200SORT_RANK_MIN"); return e ? (uint32_t)atoi(e) : (uint32_t)B200_RANK_MIN; }();
+        ca.small_max = std::min<uint32_t>((uint32_t)C::SMALL_CAP, rank_min > 0 ? rank_min - 1 : 0u);
+      }
       ca.out_buf = (uint32_t)ob;
       if (segp) { ca.seg_or = w.seg_or; ca.seg_and = w.seg_and; ca.locals_copy = w.locals[ALGO_LSD]; ca.num_copy_ptr = &ctr->num_locals[ALGO_LSD]; ca.begin_bit = begin_bit; }
       const int cgrid = (int)std::min<uint32_t>((w.max_segs + CLS_WARPS - 1) / CLS_WARPS, (uint32_t)sms * 4);
