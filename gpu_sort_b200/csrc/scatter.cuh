@@ -838,7 +838,13 @@ struct StableFastSmem {
   uint64_t dstk[PEER ? MAX_PARTS : 1], dstv[PEER ? MAX_PARTS : 1];   // PEER: base addresses of the destination buffers
   uint8_t gdst[PEER ? 2 : 1][PEER ? RADIX : 4];                      // PEER: per digit, which destination buffer
   uint32_t bsum[PEER ? RADIX : 1];                                   // PEER (inside prepare only): per bucket, keys of it in this source's earlier tiles
-  uint16_t bexcl[PEER ? RADIX : 2];                                  // PEER (inside prepare only): per bucket, where its keys start inside the tile
+  uint16_t bexcl[PEER ? RADIX + 1 : 2];                              // PEER (inside prepare only): per bucket, where its keys start inside the tile
+  // PEER, at most 32 exchange buckets: the write-out walks DESTINATION-aligned groups of 32 elements, so every warp store covers one
+  // 128-byte line of the peer's buffer (a store that straddles two lines crosses NVLink as two partial packets: 400 vs 670 GB/s,
+  // profiles/r02_ubench_peer.jsonl modes 4 / 2).  Per bucket: {first position - misalignment, start | end << 16, goff, destination};
+  // grp[b] = number of groups of the buckets before b, grp[32] = all groups of the tile.
+  alignas(16) uint4 brec[PEER ? 2 : 1][PEER ? 32 : 1];
+  uint32_t grp[PEER ? 2 : 1][PEER ? 33 : 1];
   uint32_t goff[2][RADIX];          // per digit: (global start - start inside the tile) mod 2^32; output index = goff[d] + position
   alignas(16) uint32_t match[2][WARPS * RADIX];   // per-warp match masks, two alternating sets (always zero between rows)
   alignas(16) uint16_t wcnt[WARPS * RADIX];       // per-warp counters, later per-warp start positions; zero at tile start
@@ -929,8 +935,35 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
       if (gstart) atomicAdd(&sm.bsum[PEER ? b : 0], (uint32_t)gstart);
       if ((tid & ((1u << a.xshift) - 1u)) == 0) sm.bexcl[PEER ? b : 0] = (uint16_t)excl;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      sm.goff[slot][tid] = (uint32_t)a.bins[b] + sm.bsum[PEER ? b : 0] - (uint32_t)sm.bexcl[PEER ? b : 0];
+      const uint32_t gb = (uint32_t)a.bins[b] + sm.bsum[PEER ? b : 0] - (uint32_t)sm.bexcl[PEER ? b : 0];
+      sm.goff[slot][tid] = gb;
       sm.gdst[PEER ? slot : 0][PEER ? tid : 0] = a.digit_dest[b];
+      const uint32_t nbk = (uint32_t)RADIX >> a.xshift;
+      if (nbk <= 32u) {
+        const TileGeom gg = sm.geom[slot];
+        if (tid == 0) sm.bexcl[PEER ? nbk : 0] = (uint16_t)gg.cnt;            // (padding keys rank last: real keys end at cnt)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (w == 0) {                                                          // lane = bucket
+          uint32_t ng = 0;
+          if (lane < nbk) {
+            const uint32_t s0 = sm.bexcl[PEER ? lane : 0];
+            uint32_t e0 = sm.bexcl[PEER ? lane + 1 : 0];
+            if (e0 > gg.cnt) e0 = gg.cnt;
+            const uint32_t gl = sm.goff[slot][lane << a.xshift];
+            const uint32_t mis = (gl + s0) & 31u;                              // destination index of the bucket's first element, mod 32
+            ng = e0 > s0 ? (e0 - s0 + mis + 31u) >> 5 : 0u;
+            sm.brec[PEER ? slot : 0][PEER ? lane : 0] = make_uint4(s0 - mis, s0 | (e0 << 16), gl, (uint32_t)a.digit_dest[lane]);
+          }
+          uint32_t inc = ng;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += t;
+          }
+          sm.grp[PEER ? slot : 0][PEER ? lane : 0] = inc - ng;
+          if (lane == 31) sm.grp[PEER ? slot : 0][PEER ? 32 : 0] = inc;
+        }
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");          // bsum / bexcl are reused by the next prepare
     }
   };
@@ -1053,7 +1086,26 @@ __global__ void __launch_bounds__(THREADS, OCC) scatter_stable_fast_kernel(const
     const uint32_t* __restrict__ go = sm.goff[slot];
     K* __restrict__ kout = reinterpret_cast<K*>(a.keys_out);
     V* __restrict__ vout = reinterpret_cast<V*>(a.vals_out);
-    {
+    if (PEER && ((uint32_t)RADIX >> a.xshift) <= 32u) {
+      // destination-aligned write-out: group g of the tile = 32 consecutive destination slots of one bucket, one warp store per array
+      const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
+      const bool two = a.tw_out != 0;
+      const uint32_t nbk = (uint32_t)RADIX >> a.xshift;
+      const uint32_t my_g = lane < nbk ? sm.grp[PEER ? slot : 0][PEER ? lane : 0] : 0xFFFFFFFFu;      // groups before bucket `lane`
+      const uint32_t ngroups = sm.grp[PEER ? slot : 0][PEER ? 32 : 0];
+      for (uint32_t gidx = w; gidx < ngroups; gidx += WARPS) {
+        const uint32_t b = (uint32_t)__popc(__ballot_sync(0xffffffffu, my_g <= gidx)) - 1u;           // the bucket of this group (empty buckets share a start: the last wins)
+        const uint4 r = sm.brec[PEER ? slot : 0][PEER ? b : 0];
+        const uint32_t p = r.x + ((gidx - __shfl_sync(0xffffffffu, my_g, b)) << 5) + lane;             // (r.x may be "negative": wraps back into range)
+        if ((int32_t)p >= (int32_t)(r.y & 0xFFFFu) && p < (r.y >> 16)) {
+          K k = st[p];
+          if (two) k = tw_apply_out<K>(k, sg, fl, fp);
+          const uint32_t o = r.z + p;
+          st_global<K>(reinterpret_cast<K*>(sm.dstk[PEER ? r.w : 0]), o, k);
+          if (VB) st_global<V>(reinterpret_cast<V*>(sm.dstv[PEER ? r.w : 0]), o, vst[p]);
+        }
+      }
+    } else {
       const K sg = (K)a.tw.sign_mask, fl = (K)a.tw.float_mask, fp = (K)a.tw.flip_mask;
       const bool two = a.tw_out != 0;
 #pragma unroll

@@ -157,6 +157,7 @@ int grid_for(uint64_t n, int threads) {
 //   mode 1: every warp instruction stores 512 contiguous bytes (16 bytes per lane)
 //   mode 2: 4-byte lanes, but consecutive `chunk`-byte pieces go to pseudo-random `chunk`-aligned places (a scatter's runs)
 //   mode 3: 16-byte lanes, pieces of `chunk` bytes at pseudo-random places
+//   mode 4: mode 2 with every piece shifted by 52 bytes: a warp's 128 bytes straddle two 128-byte lines (a scatter run at arbitrary alignment)
 __global__ void store_probe_kernel(uint32_t* dst, uint64_t bytes, int mode, uint32_t chunk) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
   if (mode == 0) {
@@ -166,12 +167,13 @@ __global__ void store_probe_kernel(uint32_t* dst, uint64_t bytes, int mode, uint
     for (uint64_t i = t; i < bytes / 16; i += nt) d4[i] = make_uint4((uint32_t)i, 1, 2, 3);
   } else {
     const uint64_t nchunks = bytes / chunk;            // power of two expected
-    const uint32_t per = chunk / (mode == 2 ? 4 : 16);   // lanes per chunk
-    const uint64_t units = bytes / (mode == 2 ? 4 : 16);
+    const uint32_t per = chunk / (mode != 3 ? 4 : 16);   // lanes per chunk
+    const uint64_t units = bytes / (mode != 3 ? 4 : 16);
     for (uint64_t i = t; i < units; i += nt) {
       const uint64_t c = i / per, o = i % per;
       const uint64_t pc = (c * 0x9E3779B97F4A7C15ull >> 20) & (nchunks - 1);     // scrambled chunk index (bijective enough for a bandwidth probe)
       if (mode == 2) dst[pc * (chunk / 4) + o] = (uint32_t)i;
+      else if (mode == 4) { if (pc + 1 < nchunks) dst[pc * (chunk / 4) + o + 13] = (uint32_t)i; }
       else reinterpret_cast<uint4*>(dst)[pc * (chunk / 16) + o] = make_uint4((uint32_t)i, 1, 2, 3);
     }
   }

@@ -18,8 +18,8 @@ f.restype = ctypes.c_int; f.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes
 res = []
 for target in ("local", "peer"):
     dst = ptrs[rank] if target == "local" else ptrs[(rank + 1) % world]
-    for mode, chunk in ((0, 0), (1, 0), (2, 64), (2, 128), (2, 256), (2, 512), (2, 2048), (3, 64), (3, 128), (3, 256), (3, 512), (3, 2048)):
-        for grid, block in ((148 * 2, 512), (148 * 4, 512), (148 * 8, 256)):
+    for mode, chunk in ((0, 0), (1, 0), (2, 64), (2, 128), (2, 256), (2, 512), (2, 2048), (3, 64), (3, 128), (3, 256), (3, 512), (3, 2048), (4, 128), (4, 1024), (4, 4096), (2, 1024), (2, 4096)):
+        for grid, block in ((148 * 2, 512),):
             dist.barrier(); torch.cuda.synchronize()
             ts = []
             for it in range(4):
