@@ -795,3 +795,64 @@ def test_key_range_probe_switch(gs, oracle):
     finally:
         gs.set_key_range_probe(old)
     assert same_bits(msb()[0], exp)
+
+
+@pytest.mark.parametrize("G,xbits,pairs", [(2, 1, True), (2, 4, True), (4, 2, True), (4, 5, True), (4, 6, True), (2, 8, True), (3, 4, False), (8, 3, True)])
+def test_exchange_as_level0_emulated_ranks(gs, oracle, G, xbits, pairs):
+    """The multi-GPU exchange (b200_exchange_hist -> count matrix -> b200_exchange_scatter -> b200_segmented_sort) with G ranks
+    EMULATED on one GPU: every rank's scatter runs as its own launch over its own slice and writes into G receive buffers that all
+    live on this device (the kernels never wait on one another, so this is safe on one GPU).  The concatenated result must equal
+    ONE stable sort of the concatenated input, bit for bit (SURVEY.md section 8e "Validation").  xbits <= 5 takes the
+    destination-aligned write-out, larger xbits the per-position one."""
+    import ctypes
+    kt = KT_ID["u32"]; vb = 4 if pairs else 0
+    sizes = [150_000 + 7777 * r for r in range(G)]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    total = int(offs[-1])
+    keys = raw_keys(oracle, total, "u32", seed=11)
+    keys[: total // 3] &= np.uint32(0x3FFFFFFF)                    # some skew on the exchange digit
+    vals = np.arange(total, dtype=np.uint32) if pairs else None
+    cap = int(max(sizes) * 2.5) + 4096
+    P = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+    recv_k = [torch.zeros(cap, dtype=torch.int32, device="cuda") for _ in range(G)]
+    recv_v = [torch.zeros(cap, dtype=torch.int32, device="cuda") for _ in range(G)] if pairs else None
+    dst_k = torch.tensor([t.data_ptr() for t in recv_k], dtype=torch.int64, device="cuda")
+    dst_v = torch.tensor([t.data_ptr() for t in recv_v] if pairs else [0] * G, dtype=torch.int64, device="cuda")
+    dk = [dev(keys[offs[r]:offs[r + 1]]) for r in range(G)]
+    dv = [dev(vals[offs[r]:offs[r + 1]]) for r in range(G)] if pairs else [None] * G
+    matrix = torch.zeros(G * 256, dtype=torch.int64, device="cuda")
+    temps = []
+    for r in range(G):
+        nb = ctypes.c_size_t(0)
+        gs._check(gs.lib.b200_exchange_hist(None, ctypes.byref(nb), None, sizes[r], kt, vb, xbits, None, None), "size")
+        t = torch.empty(nb.value, dtype=torch.uint8, device="cuda"); temps.append((t, nb))
+        gs._check(gs.lib.b200_exchange_hist(P(t), ctypes.byref(nb), P(dk[r]), sizes[r], kt, vb, xbits, P(matrix[r * 256:(r + 1) * 256]), None), "hist")
+    seg_b = [torch.zeros(256, dtype=torch.int64, device="cuda") for _ in range(G)]
+    seg_e = [torch.zeros(256, dtype=torch.int64, device="cuda") for _ in range(G)]
+    info = [torch.zeros(8, dtype=torch.int64, device="cuda") for _ in range(G)]
+    for r in range(G):
+        t, nb = temps[r]
+        gs._check(gs.lib.b200_exchange_scatter(P(t), ctypes.byref(nb), P(dk[r]), P(dv[r]), sizes[r], kt, vb, xbits, P(matrix), G, r, cap,
+                                               P(dst_k), P(dst_v), P(seg_b[r]), P(seg_e[r]), P(info[r]), None), "scatter")
+    torch.cuda.synchronize()
+    out_k, out_v = [], []
+    for r in range(G):
+        h = info[r].cpu().numpy()
+        assert h[1] == 0, "the plan must fit the receive capacity"
+        n_recv = int(h[0])
+        kb = gs.DoubleBuffer(recv_k[r], torch.empty_like(recv_k[r]))
+        vbuf = gs.DoubleBuffer(recv_v[r], torch.empty_like(recv_v[r])) if pairs else None
+        tb = gs.DeviceSegmentedRadixSort._run(None, kb, vbuf, cap, 256, seg_b[r], seg_e[r], 0, 32 - xbits, False, None, kt, ties_are_equal=True)
+        temp = torch.empty(tb, dtype=torch.uint8, device="cuda")
+        gs.DeviceSegmentedRadixSort._run(temp, kb, vbuf, cap, 256, seg_b[r], seg_e[r], 0, 32 - xbits, False, None, kt, ties_are_equal=True)
+        torch.cuda.synchronize()
+        assert gs.sort_status(temp) == 0
+        out_k.append(host(kb.Current(), np.uint32)[:n_recv])
+        if pairs:
+            out_v.append(host(vbuf.Current(), np.uint32)[:n_recv])
+    got_k = np.concatenate(out_k)
+    assert got_k.size == total
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(got_k, keys[order]), "keys: the ranks' results, concatenated, are the sorted global array"
+    if pairs:
+        assert np.array_equal(np.concatenate(out_v), vals[order]), "values: ONE stable sort of the concatenated input"
