@@ -479,7 +479,7 @@ __device__ __forceinline__ void hand_back(const LocalArgs& a, const LocalItem& i
 
 // SKEW: the launch serves the handed-back buckets, whose digits are known to be skewed (see lsd_sort_item).
 template <typename K, int VB, int THREADS, int IPT, int ALGO, bool STABLE, bool SKEW = false>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : THREADS == 384 ? ((VB == 0 && ALGO == ALGO_LSD) ? 3 : B200_LOCAL_OCC384) : (sizeof(LocalSmem<K, VB, THREADS, IPT, ALGO>) <= 113 * 1024 && THREADS <= 768) ? 2 : 1)) local_sort_kernel(const __grid_constant__ LocalArgs a) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? (IPT > 6 ? 3 : 4) : THREADS == 384 ? ((VB == 0 && ALGO == ALGO_LSD) ? 3 : B200_LOCAL_OCC384) : (sizeof(LocalSmem<K, VB, THREADS, IPT, ALGO>) <= 113 * 1024 && THREADS <= 768) ? 2 : 1)) local_sort_kernel(const __grid_constant__ LocalArgs a) {
   pdl_wait();
   using V = typename ValType<VB>::type;
   using SM = LocalSmem<K, VB, THREADS, IPT, ALGO>;
