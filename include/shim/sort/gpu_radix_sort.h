@@ -82,6 +82,11 @@ RDXSRT_SortedSequence<KeyT, ValueT> rdxsrt_unstable_sort(KeyT* dev_keys, ValueT*
                                pre_allocated_dm ? &bytes : nullptr, (b200_stream_t)cstrm_extsrt, &ok, &ov);
   b200shim::die_on_error(rc, "rdxsrt_unstable_sort");          // the reference exit(-1)s on failure (gpu_radix_sort.h:397-400); never return unsorted data
   b200shim::die_on_error((int)cudaStreamSynchronize(cstrm_extsrt), "rdxsrt_unstable_sort (synchronize)");
+  if (pre_allocated_dm) {        // device-side conditions (a work list of the data manager's workspace overflowed): exit like the reference
+    int status = 0;
+    b200shim::die_on_error(b200_sort_status(pre_allocated_dm->workspace, (b200_stream_t)cstrm_extsrt, &status), "rdxsrt_unstable_sort (status)");
+    if (status != 0) { fprintf(stderr, "rdxsrt_unstable_sort failed: device status %d\n", status); exit(-1); }
+  }
   RDXSRT_SortedSequence<KeyT, ValueT> r;
   r.sorted_keys = (KeyT*)ok; r.sorted_values = (ValueT*)ov;
   return r;
