@@ -118,17 +118,7 @@ __device__ __forceinline__ bool count_sort_item(K* __restrict__ sk, typename Val
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) key[j] = twiddle_in<K>(key[j], tw);
   }
-  // Early out: if more than six of a warp's first 32 keys share lane 0's cell, that cell holds about a fifth of the bucket -- far more
-  // than the 15 a counter takes -- and the counting attempt would be thrown away after its atomics (buckets of skewed inputs)
-  int suspect = 0;
-  if (cnt >= 256u) {
-    const uint32_t v0 = (uint32_t)(key[0] >> vshift) & vmask;
-    const bool valid0 = tid < cnt;
-    const uint32_t lead = __shfl_sync(0xffffffffu, v0, 0);
-    const unsigned same = __ballot_sync(0xffffffffu, valid0 && v0 == lead);
-    suspect = ((same & 1u) != 0u && __popc(same) > 6) ? 1 : 0;
-  }
-  if (__syncthreads_or(suspect)) return false;
+  __syncthreads();
   int ovf = 0;
 #pragma unroll
   for (int j = 0; j < ROWS; ++j)
